@@ -1,0 +1,256 @@
+// C-ABI glue: context, error reporting, precision dispatch and the fused render drivers
+// (render_rays nerf.py:286-323 forward; SURVEY.md §3.5 order for backward).
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+static int nt_launch_axpy(nt_ctx* ctx, int64_t n, const float* x, float* y, cudaStream_t st);
+
+void nt_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* nt_last_error(void) { return g_err; }
+extern "C" int nt_version(void) { return 100; }
+extern "C" int64_t nt_param_count(void) { return NT_N_PARAMS; }
+
+extern "C" int nt_layer_table(nt_layer_desc out[NT_N_LAYERS]) {
+  if (!out) return NT_ERR_INVALID;
+  LayerTable L = nt_layers();
+  for (int i = 0; i < NT_N_LAYERS; ++i) {
+    out[i].out_features = kLayerOut[i];
+    out[i].in_features = kLayerIn[i];
+    out[i].weight_offset = L.w[i];
+    out[i].bias_offset = L.b[i];
+  }
+  return NT_OK;
+}
+
+extern "C" int nt_create(nt_ctx** out, int device, int n_coarse, int n_fine) {
+  NT_REQUIRE(out, "null out");
+  NT_REQUIRE(n_coarse == 64 && n_fine == 128, "this build supports n_coarse=64, n_fine=128 (conf/lego.ini, conf/fern.ini)");
+  int count = 0;
+  NT_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) {
+    nt_set_error("no CUDA device %d (found %d); libnerftiny has no CPU fallback", device, count);
+    return NT_ERR_CUDA;
+  }
+  NT_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  NT_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    nt_set_error("device %d is sm_%d%d; libnerftiny is built for sm_100a only", device, prop.major, prop.minor);
+    return NT_ERR_UNSUPPORTED;
+  }
+  nt_ctx* c = new (std::nothrow) nt_ctx();
+  NT_REQUIRE(c, "out of host memory");
+  c->device = device;
+  c->n_coarse = n_coarse;
+  c->n_fine = n_fine;
+  c->sm_count = prop.multiProcessorCount;
+  c->launches = 0;
+  c->d_flags = nullptr;
+  if (cudaMalloc(&c->d_flags, 4 * sizeof(int)) != cudaSuccess || cudaMemset(c->d_flags, 0, 4 * sizeof(int)) != cudaSuccess) {
+    nt_set_error("cudaMalloc of the status flags failed");
+    delete c;
+    return NT_ERR_CUDA;
+  }
+  *out = c;
+  return NT_OK;
+}
+
+extern "C" void nt_destroy(nt_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->d_flags) cudaFree(ctx->d_flags);
+  delete ctx;
+}
+
+extern "C" int64_t nt_launch_count(const nt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- precision dispatch ------------------------------------------------------------------------
+extern "C" size_t nt_mlp_workspace_bytes(nt_ctx* ctx, int precision, int64_t n, int p, int train) {
+  (void)ctx;
+  if (precision == NT_PREC_FP32) return nt_mlp_f32_workspace_bytes(n, p, train);
+  if (precision == NT_PREC_BF16) return train ? nt_mlp_f32_workspace_bytes(n, p, 1) : 256;
+  return 0;
+}
+extern "C" size_t nt_packed_weight_bytes(nt_ctx* ctx, int precision) {
+  (void)ctx;
+  return precision == NT_PREC_BF16 ? nt_mlp_tc_packed_bytes() : 0;
+}
+extern "C" int nt_pack_weights(nt_ctx* ctx, int precision, const float* params, void* packed, void* stream) {
+  NT_REQUIRE(ctx && params, "null pointer");
+  if (precision == NT_PREC_FP32) return NT_OK;
+  NT_REQUIRE(precision == NT_PREC_BF16 && packed, "bad precision / null packed buffer");
+  return nt_mlp_tc_pack(ctx, params, packed, (cudaStream_t)stream);
+}
+
+extern "C" int nt_mlp_forward(nt_ctx* ctx, int precision, int64_t n, int p, const float* t, const float* rays,
+                              const float* dir_enc, const float* params, const void* packed, float* rgb, float* sigma,
+                              void* ws, size_t ws_bytes, int train, void* stream) {
+  NT_REQUIRE(ctx && t && rays && dir_enc && params && rgb && sigma, "null pointer");
+  NT_REQUIRE(p > 0 && n >= 0, "bad shape");
+  if (n == 0) return NT_OK;
+  if (precision == NT_PREC_FP32 || (precision == NT_PREC_BF16 && train)) {
+    // training keeps fp32 activations for the layer-major backward (bf16 training kernels: next round)
+    NT_REQUIRE(ws, "fp32 MLP needs a workspace");
+    return nt_mlp_f32_forward(ctx, n, p, t, rays, dir_enc, params, rgb, sigma, ws, ws_bytes, train, (cudaStream_t)stream);
+  }
+  if (precision == NT_PREC_BF16) {
+    NT_REQUIRE(packed, "NT_PREC_BF16 needs packed weights (nt_pack_weights)");
+    return nt_mlp_tc_forward(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, (cudaStream_t)stream);
+  }
+  nt_set_error("unknown precision %d", precision);
+  return NT_ERR_UNSUPPORTED;
+}
+
+extern "C" int nt_mlp_backward(nt_ctx* ctx, int precision, int64_t n, int p, const float* t, const float* rays,
+                               const float* dir_enc, const float* params, const void* packed, const float* g_rgb,
+                               const float* g_sigma, float* grads, float* g_t, void* ws, size_t ws_bytes, void* stream) {
+  (void)dir_enc;
+  (void)packed;
+  NT_REQUIRE(ctx && t && rays && params && g_rgb && g_sigma && grads && ws, "null pointer");
+  NT_REQUIRE(precision == NT_PREC_FP32 || precision == NT_PREC_BF16, "unknown precision");
+  if (n == 0) return NT_OK;
+  return nt_mlp_f32_backward(ctx, n, p, t, rays, params, g_rgb, g_sigma, grads, g_t, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// ---- fused render driver ---------------------------------------------------------------------------
+struct RenderWs {
+  float *rays, *dir_enc, *t_c, *rgb_c, *sig_c, *w_c, *t_f, *rgb_f, *sig_f;
+  uint8_t* perm;
+  float *g_rgb_c, *g_sig_c, *g_rgb_f, *g_sig_f, *g_t_f, *g_w_c, *g_t_mlp;
+  void *mlp_c, *mlp_f;
+  size_t mlp_c_bytes, mlp_f_bytes;
+  size_t bytes;
+};
+
+static RenderWs carve_render(nt_ctx* ctx, void* base, int precision, int64_t n, int train) {
+  RenderWs w;
+  memset(&w, 0, sizeof(w));
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t bytes) {
+    void* p = (void*)(b + off);
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  const int nc = ctx->n_coarse, nf = ctx->n_fine;
+  w.rays = (float*)take(n * 16 * 4);
+  w.dir_enc = (float*)take(n * 24 * 4);
+  w.t_c = (float*)take(n * nc * 4);
+  w.rgb_c = (float*)take(n * nc * 12);
+  w.sig_c = (float*)take(n * nc * 4);
+  w.w_c = (float*)take(n * nc * 4);
+  w.t_f = (float*)take(n * nf * 4);
+  w.rgb_f = (float*)take(n * nf * 12);
+  w.sig_f = (float*)take(n * nf * 4);
+  w.mlp_c_bytes = nt_mlp_workspace_bytes(ctx, precision, n, nc, train);
+  w.mlp_f_bytes = nt_mlp_workspace_bytes(ctx, precision, n, nf, train);
+  if (train) {
+    w.perm = (uint8_t*)take(n * 5 * (nc + nf));
+    w.g_rgb_c = (float*)take(n * nc * 12);
+    w.g_sig_c = (float*)take(n * nc * 4);
+    w.g_rgb_f = (float*)take(n * nf * 12);
+    w.g_sig_f = (float*)take(n * nf * 4);
+    w.g_t_f = (float*)take(n * nf * 4);
+    w.g_w_c = (float*)take(n * nc * 4);
+    w.g_t_mlp = (float*)take(n * nf * 4);
+    w.mlp_c = take(w.mlp_c_bytes);
+    w.mlp_f = take(w.mlp_f_bytes);
+  } else {
+    size_t m = w.mlp_c_bytes > w.mlp_f_bytes ? w.mlp_c_bytes : w.mlp_f_bytes;
+    w.mlp_c = w.mlp_f = take(m);
+  }
+  w.bytes = off;
+  return w;
+}
+
+extern "C" size_t nt_render_workspace_bytes(nt_ctx* ctx, int precision, int64_t n, int train) {
+  if (!ctx || n < 0) return 0;
+  return carve_render(ctx, nullptr, precision, n, train).bytes;
+}
+
+#define NT_TRY(x)                   \
+  do {                              \
+    int rc__ = (x);                 \
+    if (rc__ != NT_OK) return rc__; \
+  } while (0)
+
+extern "C" int nt_render_forward(nt_ctx* ctx, int precision, int64_t n, const int64_t* row, const int64_t* col,
+                                 const float* c2w, int c2w_stride, const float* kinv, const float* near_,
+                                 const float* far_, const float* params, const void* packed, int any_step_zero,
+                                 const float* delta0, float* c_coarse, float* c_fine, void* ws, size_t ws_bytes,
+                                 int train, void* stream) {
+  NT_REQUIRE(ctx && row && col && c2w && kinv && near_ && far_ && params && c_coarse && c_fine && ws, "null pointer");
+  if (n <= 0) return NT_OK;
+  RenderWs w = carve_render(ctx, ws, precision, n, train);
+  if (ws_bytes < w.bytes) {
+    nt_set_error("render workspace too small: have %zu need %zu", ws_bytes, w.bytes);
+    return NT_ERR_WORKSPACE;
+  }
+  const int nc = ctx->n_coarse, nf = ctx->n_fine;
+  NT_TRY(nt_raygen(ctx, n, row, col, c2w, c2w_stride, kinv, w.rays, nullptr, w.dir_enc, stream));
+  NT_TRY(nt_sample_coarse(ctx, n, near_, far_, any_step_zero, w.t_c, stream));                         // nerf.py:288
+  NT_TRY(nt_mlp_forward(ctx, precision, n, nc, w.t_c, w.rays, w.dir_enc, params, packed, w.rgb_c, w.sig_c, w.mlp_c,
+                        w.mlp_c_bytes, train, stream));                                                // nerf.py:289
+  NT_TRY(nt_composite_coarse(ctx, n, near_, far_, w.rgb_c, w.sig_c, w.w_c, c_coarse, stream));         // nerf.py:293-295, 320
+  NT_TRY(nt_sample_pdf(ctx, n, w.t_c, w.w_c, delta0, w.t_f, nullptr, stream));                         // nerf.py:298
+  NT_TRY(nt_mlp_forward(ctx, precision, n, nf, w.t_f, w.rays, w.dir_enc, params, packed, w.rgb_f, w.sig_f, w.mlp_f,
+                        w.mlp_f_bytes, train, stream));                                                // nerf.py:299
+  NT_TRY(nt_composite_fine(ctx, n, w.t_c, w.rgb_c, w.sig_c, w.t_f, w.rgb_f, w.sig_f, 1e-4f, c_fine, nullptr,
+                           train ? w.perm : nullptr, stream));                                         // nerf.py:302-321
+  return NT_OK;
+}
+
+extern "C" int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const float* near_, const float* far_,
+                                  const float* params, const void* packed, const float* delta0,
+                                  const float* g_c_coarse, const float* g_c_fine, float* grads, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  NT_REQUIRE(ctx && near_ && far_ && params && g_c_coarse && g_c_fine && grads && ws, "null pointer");
+  if (n <= 0) return NT_OK;
+  RenderWs w = carve_render(ctx, ws, precision, n, 1);
+  if (ws_bytes < w.bytes) {
+    nt_set_error("render workspace too small: have %zu need %zu", ws_bytes, w.bytes);
+    return NT_ERR_WORKSPACE;
+  }
+  const int nc = ctx->n_coarse, nf = ctx->n_fine;
+  // C_fine <- sort/composite (B.2, B.3)
+  NT_TRY(nt_composite_fine_backward(ctx, n, w.t_c, w.rgb_c, w.sig_c, w.t_f, w.rgb_f, w.sig_f, 1e-4f, w.perm, g_c_fine,
+                                    w.g_rgb_c, w.g_sig_c, w.g_rgb_f, w.g_sig_f, w.g_t_f, stream));
+  // fine MLP: dW + input gradient down to t_fine (B.4, B.6, B.7)
+  NT_TRY(nt_mlp_backward(ctx, precision, n, nf, w.t_f, w.rays, w.dir_enc, params, packed, w.g_rgb_f, w.g_sig_f, grads,
+                         w.g_t_mlp, w.mlp_f, w.mlp_f_bytes, stream));
+  // g_t_fine = compositing path + MLP-input path; then resample backward (B.5)
+  NT_TRY(nt_launch_axpy(ctx, n * nf, w.g_t_mlp, w.g_t_f, (cudaStream_t)stream));
+  NT_TRY(nt_sample_pdf_backward(ctx, n, w.t_c, w.w_c, delta0, w.g_t_f, w.g_w_c, stream));
+  // C_coarse <- composite; rgb/sigma of the coarse samples also feed the fine composite: add both
+  float* g_rgb_c2 = w.g_rgb_f;  // fine-pass buffers are free again: reuse as scratch for the coarse composite grads
+  float* g_sig_c2 = w.g_sig_f;
+  NT_TRY(nt_composite_coarse_backward(ctx, n, near_, far_, w.rgb_c, w.sig_c, g_c_coarse, w.g_w_c, g_rgb_c2, g_sig_c2,
+                                      stream));
+  NT_TRY(nt_launch_axpy(ctx, n * nc * 3, g_rgb_c2, w.g_rgb_c, (cudaStream_t)stream));
+  NT_TRY(nt_launch_axpy(ctx, n * nc, g_sig_c2, w.g_sig_c, (cudaStream_t)stream));
+  // coarse MLP: dW only (t_coarse is a constant)
+  NT_TRY(nt_mlp_backward(ctx, precision, n, nc, w.t_c, w.rays, w.dir_enc, params, packed, w.g_rgb_c, w.g_sig_c, grads,
+                         nullptr, w.mlp_c, w.mlp_c_bytes, stream));
+  return NT_OK;
+}
+
+__global__ void axpy_kernel(int64_t n, const float* __restrict__ x, float* __restrict__ y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+static int nt_launch_axpy(nt_ctx* ctx, int64_t n, const float* x, float* y, cudaStream_t st) {
+  if (n <= 0) return NT_OK;
+  axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, x, y);
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}

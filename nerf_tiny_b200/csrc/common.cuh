@@ -1,0 +1,122 @@
+// Shared declarations for libnerftiny (sm_100a).  Host+device helpers, the layer table and
+// the internal launch functions each .cu file exports to api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/nerftiny.h"
+
+#define NT_WARP 32
+#define NT_MAX_COARSE 64
+#define NT_MAX_FINE 128
+
+struct nt_ctx {
+  int device;
+  int n_coarse, n_fine;
+  int sm_count;
+  int* d_flags;  // [0] = any_step_zero scratch, [1] = resample range status
+  int64_t launches;
+};
+
+void nt_set_error(const char* fmt, ...);
+
+#define NT_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      nt_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));  \
+      return NT_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define NT_LAUNCH_CHECK(ctx)                                                               \
+  do {                                                                                     \
+    (ctx)->launches++;                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess) {                                                              \
+      nt_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return NT_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define NT_REQUIRE(cond, msg)                                                              \
+  do {                                                                                     \
+    if (!(cond)) {                                                                         \
+      nt_set_error("%s:%d invalid argument: %s", __FILE__, __LINE__, msg);                 \
+      return NT_ERR_INVALID;                                                               \
+    }                                                                                      \
+  } while (0)
+
+// ---- layer table (nerf.py:85-99) --------------------------------------------------------
+enum { L_P0 = 0, L_P1, L_P2, L_P3, L_P4, L_P5, L_P6, L_P7, L_SIGMA, L_INFO, L_DIR, L_COLOR };
+static const int kLayerOut[NT_N_LAYERS] = {256, 256, 256, 256, 256, 256, 256, 256, 1, 256, 128, 3};
+static const int kLayerIn[NT_N_LAYERS] = {60, 256, 256, 256, 316, 256, 256, 256, 256, 256, 280, 128};
+
+struct LayerTable {
+  int64_t w[NT_N_LAYERS], b[NT_N_LAYERS];
+};
+static inline LayerTable nt_layers() {
+  LayerTable t;
+  int64_t off = 0;
+  for (int i = 0; i < NT_N_LAYERS; ++i) {
+    t.w[i] = off;
+    off += (int64_t)kLayerOut[i] * kLayerIn[i];
+    t.b[i] = off;
+    off += kLayerOut[i];
+  }
+  return t;
+}
+
+// ---- encoder frequencies (nerf.py:141-145; SURVEY.md Appendix A.4, fp32 bit patterns) -------
+#define NT_FREQ_POINT_INIT                                                                       \
+  {0x40490fdbu, 0x40d928aeu, 0x416a8b6cu, 0x41fd527bu, 0x4288cd33u, 0x4313c0fau, 0x439f953cu,   \
+   0x442c5befu, 0x44ba2881u, 0x45490fdbu}
+#define NT_FREQ_DIR_INIT {0x40490fdbu, 0x40fd527au, 0x419f953cu, 0x42490fdbu}
+
+// ---- internal launchers (one per .cu) ---------------------------------------------------------
+// geom.cu
+int nt_launch_encode_points(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, float* enc, int ld_enc,
+                            cudaStream_t st);
+int nt_launch_expand_dir_enc(nt_ctx* ctx, int64_t n, int p, const float* dir_enc, float* out, int ld, cudaStream_t st);
+int nt_launch_encode_backward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* g_enc,
+                              int ld, float* g_t, cudaStream_t st);
+
+// gemm_f32.cu
+struct GemmSeg {
+  const float* A;
+  int lda;
+  const float* B;
+  int ldb;
+  int K;
+};
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ABS = 2, ACT_SIGMOID = 3 };
+struct GemmEpi {
+  const float* bias;   // [N] or null
+  int act;             // ACT_*
+  const float* mask;   // [M, ldmask]: out = mask>0 ? acc : 0  (null = none)
+  int ldmask;
+  int accumulate;      // C += result
+  int atomic;          // atomicAdd into C (split-K)
+  float* pre_out;      // optional: pre-activation copy (ACT_ABS backward needs the sign)
+  int ldpre;
+};
+// C[M,N] = epi(sum_seg A_seg op B_seg).  a_km: A stored [K][M] (else [M][K]); b_kn: B stored [K][N] (else [N][K]).
+int nt_launch_gemm(nt_ctx* ctx, int M, int N, GemmSeg s0, GemmSeg s1, bool a_km, bool b_kn, float* C, int ldc,
+                   GemmEpi epi, int split_k, cudaStream_t st);
+int nt_launch_colsum(nt_ctx* ctx, const float* G, int64_t rows, int cols, int ld, float* out, cudaStream_t st);
+
+// mlp_f32.cu
+size_t nt_mlp_f32_workspace_bytes(int64_t n, int p, int train);
+int nt_mlp_f32_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                       const float* params, float* rgb, float* sigma, void* ws, size_t ws_bytes, int train,
+                       cudaStream_t st);
+int nt_mlp_f32_backward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* params,
+                        const float* g_rgb, const float* g_sigma, float* grads, float* g_t, void* ws, size_t ws_bytes,
+                        cudaStream_t st);
+
+// mlp_tc.cu (tcgen05 / TMEM fused encode+MLP, bf16 operands)
+size_t nt_mlp_tc_packed_bytes();
+int nt_mlp_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t st);
+int nt_mlp_tc_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                      const float* params, const void* packed, float* rgb, float* sigma, cudaStream_t st);

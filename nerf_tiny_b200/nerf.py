@@ -1,0 +1,508 @@
+"""Drop-in for the reference's `nerf.py` module surface, backed by libnerftiny.so.
+
+Same names, positional order and defaults as the reference:
+  seed_everything (nerf.py:43), poses_extract (:52), Activation (:69), Network (:76), Encoder (:126),
+  NeRFModel (:169) with net_out / resample / get_density / color_cum / render_rays / ray_loss / forward,
+  NeRFRunner (:353).  Module globals `device` and `writer` behave as in nerf.py:39-40.
+
+PyTorch is used here for device memory, streams, parameter bookkeeping and autograd *plumbing* only;
+every arithmetic step of the hot path runs in the hand-written CUDA kernels behind the C-ABI
+(include/nerftiny.h).  There is no CPU fallback: constructing a NeRFModel without the shared library or
+without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import random
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+writer = None
+device = None
+
+PRECISION = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+
+
+def seed_everything(seed):
+    """nerf.py:43-48."""
+    os.environ["PL_GLOBAL_SEED"] = str(seed)
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def poses_extract(pb_matrix):
+    """nerf.py:52-67: [N,17] -> (c_to_w [N,4,4], H, W, focal, near [N], far [N]); pure data movement."""
+    n = pb_matrix.shape[0]
+    pose = pb_matrix[:, :-2].reshape(-1, 3, 5)
+    bottom = torch.zeros(n, 1, 4, dtype=pb_matrix.dtype, device=pb_matrix.device)
+    bottom[:, 0, 3] = 1.0
+    c_to_w = torch.cat((pose[:, :, :-1], bottom), dim=1)
+    return c_to_w, pose[0, 0, -1], pose[0, 1, -1], pose[0, 2, -1], pb_matrix[:, -2], pb_matrix[:, -1]
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f32(t, dev):
+    return t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+class Activation(nn.Module):
+    """nerf.py:69-74 (sigma = |x|).  Fused into the MLP kernels; kept for state_dict/module-tree parity."""
+
+    def forward(self, x):
+        raise _lib.NerfTinyError("Activation is fused into the CUDA MLP kernels; call Network/NeRFModel instead")
+
+
+class Network(nn.Module):
+    """nerf.py:76-99: same module tree, hence the same state_dict keys and nn.Linear default init.
+
+    All 24 tensors are views into ONE flat fp32 buffer in state_dict order (the layout the C-ABI uses), so the
+    fused Adam and the gradient all-reduce each touch a single 2.4 MB buffer.
+    """
+
+    def __init__(self, point_dim=60, dir_dim=24, depth=8, width=256, batch_size=8, layers_skip=[4]):
+        super().__init__()
+        if (point_dim, dir_dim, depth, width, list(layers_skip)) != (60, 24, 8, 256, [4]):
+            raise _lib.NerfTinyError("libnerftiny is built for the 8x256 skip-4 network of nerf.py:77")
+        self.depth, self.width, self.batch_size, self.layers_skip = depth, width, batch_size, layers_skip
+        self.point_layer = nn.ModuleList([nn.Sequential(nn.Linear(point_dim, width), nn.ReLU(True))])
+        for i in range(1, depth):
+            fan_in = width + point_dim if i in layers_skip else width
+            self.point_layer.append(nn.Sequential(nn.Linear(fan_in, width), nn.ReLU(True)))
+        self.sigma_layer = nn.Sequential(nn.Linear(width, 1), Activation())
+        self.point_info = nn.Linear(width, width)
+        self.dir_info = nn.Sequential(nn.Linear(width + dir_dim, width // 2), nn.ReLU(True))
+        self.color_layer = nn.Sequential(nn.Linear(width // 2, 3), nn.Sigmoid())
+        self._flat = None
+        self._flat_grad = None
+        self._flatten()
+
+    # -- flat parameter storage ------------------------------------------------------------------
+    def _flatten(self, dev=None):
+        params = list(self.parameters())
+        dev = dev if dev is not None else params[0].device
+        flat = torch.empty(_lib.N_PARAMS, dtype=torch.float32, device=dev)
+        grad = torch.zeros(_lib.N_PARAMS, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            n = p.numel()
+            flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + n].view(p.shape)
+            p.grad = grad[off:off + n].view(p.shape)
+            off += n
+        assert off == _lib.N_PARAMS
+        self._flat, self._flat_grad = flat, grad
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._flatten()
+        return out
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self._flatten()
+        return out
+
+    def flat_params(self):
+        p0 = next(self.parameters())
+        if p0.data_ptr() != self._flat.data_ptr() or p0.device != self._flat.device:
+            self._flatten()
+        return self._flat
+
+    def flat_grads(self):
+        """Gather .grad into the flat buffer (no copy when the grads are already its views)."""
+        off = 0
+        for p in self.parameters():
+            n = p.numel()
+            g = p.grad
+            if g is None:
+                self._flat_grad[off:off + n].zero_()
+                p.grad = self._flat_grad[off:off + n].view(p.shape)
+            elif g.data_ptr() != self._flat_grad.data_ptr() + 4 * off:
+                self._flat_grad[off:off + n].copy_(g.reshape(-1))
+                p.grad = self._flat_grad[off:off + n].view(p.shape)
+            off += n
+        return self._flat_grad
+
+    def forward(self, num_points, point, dir):
+        raise _lib.NerfTinyError(
+            "Network.forward on pre-computed encodings is not part of the fused path; use NeRFModel.net_out")
+
+
+class Encoder(nn.Module):
+    """nerf.py:126-167.  The sin/cos features are generated inside the MLP kernels (never materialised);
+    the class is kept so the module tree matches.  Like the reference it has no parameters."""
+
+    def __init__(self, L_point=10, L_dir=4, batch_size=8):
+        super().__init__()
+        if (L_point, L_dir) != (10, 4):
+            raise _lib.NerfTinyError("libnerftiny is built for L_point=10, L_dir=4 (nerf.py:127)")
+        self.L_point, self.L_dir, self.batch_size = L_point, L_dir, batch_size
+
+    def forward(self, num_points, point, dir):
+        raise _lib.NerfTinyError("Encoder.forward is fused into the CUDA MLP kernels; use NeRFModel.net_out")
+
+
+class _RenderFn(torch.autograd.Function):
+    """render_rays forward/backward as one autograd node (nerf.py:286-323 + nerf.py:473)."""
+
+    @staticmethod
+    def forward(ctx, model, flat, row, col, pose17, kinv, near, far):
+        cc, cf, ws = model._render_raw(flat, row, col, pose17, kinv, near, far, train=True)
+        ctx.model, ctx.ws, ctx.near, ctx.far, ctx.flat = model, ws, near, far, flat
+        return cc, cf
+
+    @staticmethod
+    def backward(ctx, g_cc, g_cf):
+        m = ctx.model
+        grads = torch.zeros_like(ctx.flat)
+        n = ctx.near.shape[0]
+        g_cc = g_cc.contiguous().float()
+        g_cf = g_cf.contiguous().float()
+        _lib.check(m._lib.nt_render_backward(m._ctx, m._prec_train, n, _ptr(ctx.near), _ptr(ctx.far), _ptr(ctx.flat),
+                                             _ptr(m._packed), None, _ptr(g_cc), _ptr(g_cf), _ptr(grads), _ptr(ctx.ws),
+                                             ctx.ws.numel(), _stream()))
+        ctx.ws = None
+        return None, grads, None, None, None, None, None, None
+
+
+class NeRFModel(nn.Module):
+    """nerf.py:169-348.  `precision` ("bf16" tcgen05 path / "fp32" accuracy path) is the one extra knob."""
+
+    def __init__(self, num_coarse=64, num_fine=128, batch_ray=8, precision=None):
+        super().__init__()
+        self.encoder = Encoder(batch_size=batch_ray)
+        self.network = Network(batch_size=batch_ray)
+        self.num_coarse, self.num_fine, self.batch_ray = num_coarse, num_fine, batch_ray
+        self.precision = precision or os.environ.get("NERF_TINY_PRECISION", "bf16")
+        self._lib = _lib.load()          # raises if the extension is missing: no fallback
+        self._ctx = None
+        self._packed = None
+        self._ws_cache = {}
+        self.check_range = True          # raise (the reference: exit(0)) right after forward
+
+    # -- context -----------------------------------------------------------------------------------
+    def _ensure_ctx(self):
+        dev = self.network.flat_params().device
+        if dev.type != "cuda":
+            raise _lib.NerfTinyError("NeRFModel lives on %s: move it to a CUDA device (no CPU path exists)" % dev)
+        if self._ctx is None or self._ctx_dev != dev:
+            h = C.c_void_p()
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            _lib.check(self._lib.nt_create(C.byref(h), idx, self.num_coarse, self.num_fine))
+            self._ctx, self._ctx_dev = h, dev
+            self._packed = torch.empty(max(256, self._lib.nt_packed_weight_bytes(h, _lib.PREC_BF16)), dtype=torch.uint8,
+                                       device=dev)
+        return dev
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None) is not None:
+                self._lib.nt_destroy(self._ctx)
+        except Exception:
+            pass
+
+    @property
+    def _prec(self):
+        return PRECISION[self.precision]
+
+    @property
+    def _prec_train(self):
+        return PRECISION[self.precision]
+
+    @property
+    def launch_count(self):
+        return int(self._lib.nt_launch_count(self._ctx)) if self._ctx is not None else 0
+
+    def _workspace(self, n, train):
+        need = self._lib.nt_render_workspace_bytes(self._ctx, self._prec, n, 1 if train else 0)
+        if train:   # owned by the autograd node
+            return torch.empty(need, dtype=torch.uint8, device=self._ctx_dev)
+        ws = self._ws_cache.get("render")
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=self._ctx_dev)
+            self._ws_cache["render"] = ws
+        return ws
+
+    def _pack(self, flat):
+        if self._prec == _lib.PREC_BF16:
+            _lib.check(self._lib.nt_pack_weights(self._ctx, self._prec, _ptr(flat), _ptr(self._packed), _stream()))
+
+    def _render_raw(self, flat, row, col, pose17, kinv, near, far, train, any_step_zero=-1, delta0=None):
+        n = row.shape[0]
+        dev = self._ctx_dev
+        cc = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        cf = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        ws = self._workspace(n, train)
+        self._pack(flat)
+        stride = 17 if pose17.shape[-1] == 17 else pose17[0].numel()
+        _lib.check(self._lib.nt_render_forward(self._ctx, self._prec, n, _ptr(row), _ptr(col), _ptr(pose17), stride,
+                                               _ptr(kinv), _ptr(near), _ptr(far), _ptr(flat), _ptr(self._packed),
+                                               any_step_zero, _ptr(delta0), _ptr(cc), _ptr(cf), _ptr(ws), ws.numel(),
+                                               1 if train else 0, _stream()))
+        return cc, cf, ws
+
+    # -- reference methods -----------------------------------------------------------------------------
+    def render_rays(self, batch_hor, batch_ver, trans_mat, K_inv, near, far, last=0.0001):
+        """nerf.py:286-323.  trans_mat [N,4,4] (or fp32 pose rows [N,17]); near/far [N]."""
+        dev = self._ensure_ctx()
+        if last != 0.0001:
+            raise _lib.NerfTinyError("render_rays: `last` is fixed at 1e-4 in the fused driver (nerf.py:286)")
+        row = batch_hor.to(dev, non_blocking=True).to(torch.int64).contiguous()
+        col = batch_ver.to(dev, non_blocking=True).to(torch.int64).contiguous()
+        pose = _dev_f32(trans_mat, dev)
+        kinv = _dev_f32(K_inv, dev)
+        near = _dev_f32(near, dev)
+        far = _dev_f32(far, dev)
+        flat = self.network.flat_params()
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.network.parameters())
+        if needs_grad:
+            cc, cf = _RenderFn.apply(self, _FlatView.apply(flat, *self.network.parameters()), row, col, pose, kinv, near, far)
+        else:
+            cc, cf, _ = self._render_raw(flat, row, col, pose, kinv, near, far, train=False)
+        if self.check_range:
+            _lib.check(self._lib.nt_check_status(self._ctx, _stream()))
+        return cc, cf
+
+    def forward(self, row, column, poses_bound, K_inv):
+        """nerf.py:333-348: row/column int64 [N] and poses_bound float64 [N,17] arrive on the CPU from the loader."""
+        dev = self._ensure_ctx()
+        pb = poses_bound.to(dev, non_blocking=True).to(torch.float32).contiguous()   # nerf.py:338
+        near = pb[:, 15].contiguous()
+        far = pb[:, 16].contiguous()
+        return self.render_rays(row, column, pb, K_inv, near, far)
+
+    def ray_loss(self, C_coarse, C_fine, C_true):
+        """nerf.py:325-331.  Differentiable (autograd seeds 2(C-Ct) for the render node)."""
+        return _RayLossFn.apply(self, C_coarse, C_fine, C_true.to(C_coarse.device, torch.float32))
+
+    def check_status(self):
+        _lib.check(self._lib.nt_check_status(self._ctx, _stream()))
+
+    # -- piecewise methods (same math, single kernels) ---------------------------------------------
+    def net_out(self, t_array, batch_x, batch_y, trans_mat, K_inv, num_points):
+        """nerf.py:179-222 -> (color [N,P,3], sigma [N,P,1]); no autograd (use forward for training)."""
+        dev = self._ensure_ctx()
+        n = t_array.shape[0]
+        t = _dev_f32(t_array, dev)
+        row = batch_x.to(dev).to(torch.int64).contiguous()
+        col = batch_y.to(dev).to(torch.int64).contiguous()
+        pose = _dev_f32(trans_mat, dev)
+        kinv = _dev_f32(K_inv, dev)
+        rays = torch.empty(n, 16, device=dev)
+        denc = torch.empty(n, 24, device=dev)
+        stride = 17 if pose.shape[-1] == 17 else pose[0].numel()
+        _lib.check(self._lib.nt_raygen(self._ctx, n, _ptr(row), _ptr(col), _ptr(pose), stride, _ptr(kinv), _ptr(rays), None,
+                                       _ptr(denc), _stream()))
+        rgb = torch.empty(n, num_points, 3, device=dev)
+        sigma = torch.empty(n, num_points, 1, device=dev)
+        flat = self.network.flat_params()
+        self._pack(flat)
+        need = self._lib.nt_mlp_workspace_bytes(self._ctx, self._prec, n, num_points, 0)
+        ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        _lib.check(self._lib.nt_mlp_forward(self._ctx, self._prec, n, num_points, _ptr(t), _ptr(rays), _ptr(denc), _ptr(flat),
+                                            _ptr(self._packed), _ptr(rgb), _ptr(sigma), _ptr(ws), ws.numel(), 0, _stream()))
+        return rgb, sigma
+
+    def resample(self, t_coarse, dense_coarse):
+        """nerf.py:225-261 -> t_fine [N,Nf]; raises ResampleRangeError where the reference exits."""
+        dev = self._ensure_ctx()
+        t = _dev_f32(t_coarse, dev)
+        w = _dev_f32(dense_coarse, dev)
+        out = torch.empty(t.shape[0], self.num_fine, device=dev)
+        _lib.check(self._lib.nt_sample_pdf(self._ctx, t.shape[0], _ptr(t), _ptr(w), None, _ptr(out), None, _stream()))
+        self.check_status()
+        return out
+
+
+class _FlatView(torch.autograd.Function):
+    """Identity on the flat buffer whose backward scatters the flat gradient to the 24 parameters."""
+
+    @staticmethod
+    def forward(ctx, flat, *params):
+        ctx.shapes = [p.shape for p in params]
+        return flat.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, off = [], 0
+        for s in ctx.shapes:
+            n = math.prod(s)
+            outs.append(g[off:off + n].view(s))
+            off += n
+        return (None, *outs)
+
+
+class _RayLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, cc, cf, ct):
+        n = cc.shape[0]
+        loss = torch.empty(1, dtype=torch.float32, device=cc.device)
+        g_cc = torch.empty_like(cc)
+        g_cf = torch.empty_like(cf)
+        cc, cf, ct = cc.contiguous(), cf.contiguous(), ct.contiguous()
+        _lib.check(model._lib.nt_ray_loss(model._ctx, n, _ptr(cc), _ptr(cf), _ptr(ct), _ptr(loss), _ptr(g_cc), _ptr(g_cf),
+                                          _stream()))
+        ctx.save_for_backward(g_cc, g_cf)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        g_cc, g_cf = ctx.saved_tensors
+        return None, g_cc * g, g_cf * g, None
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam as configured at nerf.py:425, as ONE kernel over the flat buffers (nt_adam_step)."""
+
+    def __init__(self, model: NeRFModel, lr=1e-3, betas=(0.9, 0.999), eps=1e-7, initial_lr=None):
+        group = {"params": list(model.network.parameters()), "lr": lr, "betas": betas, "eps": eps}
+        group["initial_lr"] = lr if initial_lr is None else initial_lr
+        super().__init__([group], dict(lr=lr, betas=betas, eps=eps))
+        self.model = model
+        self.step_count = 0
+        self.m = None
+        self.v = None
+
+    def zero_grad(self, set_to_none=False):
+        net = self.model.network
+        net.flat_grads().zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        model = self.model
+        model._ensure_ctx()
+        net = model.network
+        flat, grad = net.flat_params(), net.flat_grads()
+        if self.m is None or self.m.device != flat.device:
+            self.m = torch.zeros_like(flat)
+            self.v = torch.zeros_like(flat)
+        self.step_count += 1
+        g = self.param_groups[0]
+        _lib.check(model._lib.nt_adam_step(model._ctx, flat.numel(), _ptr(flat), _ptr(grad), _ptr(self.m), _ptr(self.v),
+                                           float(g["lr"]), g["betas"][0], g["betas"][1], g["eps"], self.step_count, 1.0,
+                                           _stream()))
+
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["fused"] = {"step": self.step_count, "m": self.m, "v": self.v}
+        return sd
+
+    def load_state_dict(self, sd):
+        fused = sd.pop("fused", None)
+        super().load_state_dict(sd)
+        if fused is not None:
+            self.step_count, self.m, self.v = fused["step"], fused["m"], fused["v"]
+
+
+def train_step(model: NeRFModel, optimizer: FusedAdam, row, column, pix_val, poses_bound, K_inv,
+               grad_allreduce=None):
+    """One iteration of the reference loop body nerf.py:464-475 without autograd bookkeeping:
+    forward(train) -> ray_loss -> backward -> [all-reduce] -> fused Adam.  Returns (loss, C_coarse, C_fine)
+    as device tensors (no host sync)."""
+    dev = model._ensure_ctx()
+    L = model._lib
+    n = row.shape[0]
+    pb = poses_bound.to(dev, non_blocking=True).to(torch.float32).contiguous()
+    rowd = row.to(dev, non_blocking=True).to(torch.int64).contiguous()
+    cold = column.to(dev, non_blocking=True).to(torch.int64).contiguous()
+    ct = pix_val.to(dev, non_blocking=True).to(torch.float32).contiguous()
+    kinv = _dev_f32(K_inv, dev)
+    near, far = pb[:, 15].contiguous(), pb[:, 16].contiguous()
+    net = model.network
+    flat, grads = net.flat_params(), net.flat_grads()
+    grads.zero_()                                                     # optimizer.zero_grad() (nerf.py:467)
+    cc, cf, ws = model._render_raw(flat, rowd, cold, pb, kinv, near, far, train=True)     # nerf.py:470
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    g_cc, g_cf = torch.empty_like(cc), torch.empty_like(cf)
+    _lib.check(L.nt_ray_loss(model._ctx, n, _ptr(cc), _ptr(cf), _ptr(ct), _ptr(loss), _ptr(g_cc), _ptr(g_cf), _stream()))
+    _lib.check(L.nt_render_backward(model._ctx, model._prec_train, n, _ptr(near), _ptr(far), _ptr(flat), _ptr(model._packed),
+                                    None, _ptr(g_cc), _ptr(g_cf), _ptr(grads), _ptr(ws), ws.numel(), _stream()))
+    if grad_allreduce is not None:
+        grad_allreduce(grads)
+    optimizer.step()                                                  # nerf.py:474
+    return loss, cc, cf
+
+
+# ----------------------------------------------------------------------------------------------------
+# NeRFRunner (nerf.py:353-530): constructor signature and trainer/display call surface.  The dataset /
+# TensorBoard / image-writing shell around the hot path is out of scope this round (SURVEY.md §8(f) rows
+# f1-f3): a runner is built from any object exposing the loader's batch tuples.
+# ----------------------------------------------------------------------------------------------------
+class NeRFRunner():
+    def __init__(self, gpu=0, img_dir=None, results_path="./results/", ckpt_path="./checkpoint/", low_res=1,
+                 total_iter=100000, batch_ray=400, learning=1e-3, lr_gamma=0.1, lr_milestone=[10, 200], n_coarse=64,
+                 n_fine=128, data_type="llff", step=100, decay_end=200000, sched="EXP", continue_=False,
+                 train_batches=None, disp_batches=None, height=None, width=None, focal=None, num_pic=1,
+                 precision=None):
+        global device, writer
+        if not torch.cuda.is_available():
+            raise _lib.NerfTinyError("NeRFRunner needs a CUDA device: the B200 path has no CPU fallback")
+        device = torch.device("cuda:" + str(gpu))
+        print("Using device", device)
+        self.start_time = time.strftime("%m-%d-%H-%M-%S", time.localtime())
+        self.model = NeRFModel(num_coarse=n_coarse, num_fine=n_fine, batch_ray=batch_ray, precision=precision).to(device)
+        self.results_path, self.ckpt_path, self.low_res = results_path, ckpt_path, low_res
+        self.total_iter, self.batch_ray, self.step, self.decay_end = total_iter, batch_ray, step, decay_end
+        self.last_iter = -1
+        if train_batches is None and img_dir is not None:
+            raise _lib.NerfTinyError("image-folder datasets (loader.NeRFDataset) are outside this round's scope; "
+                                     "pass train_batches=/disp_batches= iterables of loader-shaped tuples")
+        self.train_dataloader = train_batches
+        self.val_dataloader = train_batches
+        self.disp_dataloader = disp_batches
+        self.optimizer = FusedAdam(self.model, lr=learning, betas=(0.9, 0.999), eps=1e-7, initial_lr=learning)
+        lam = (lambda it: lr_gamma ** (it / decay_end) if it < decay_end else lr_gamma * learning)   # nerf.py:426
+        self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, lr_lambda=lam, last_epoch=self.last_iter) \
+            if sched == "EXP" else torch.optim.lr_scheduler.MultiStepLR(self.optimizer, lr_milestone, lr_gamma,
+                                                                         last_epoch=self.last_iter)
+        self.height, self.width, self.focal, self.num_pic = height, width, focal, num_pic
+        if height is not None:
+            self.K_inv = torch.tensor([[1.0, 0.0, -0.5 * width], [0.0, -1.0, 0.5 * height], [0.0, 0.0, -focal]]
+                                      ).to(torch.float).transpose(0, 1)                               # nerf.py:433
+        self.losses = []
+
+    def trainer(self, mode):
+        """nerf.py:445-499 loop body (forward, ray_loss, backward, Adam, scheduler) over the batch source."""
+        dataloader = getattr(self, mode + "_dataloader")
+        it = self.last_iter + 1
+        while it < self.total_iter:
+            n_seen = 0
+            for (row, column, pix_val, poses_bound, pic) in dataloader:
+                loss, _, _ = train_step(self.model, self.optimizer, row, column, pix_val, poses_bound, self.K_inv)
+                self.scheduler.step()
+                self.losses.append(loss)
+                it += 1
+                n_seen += 1
+                if it >= self.total_iter:
+                    break
+            if mode == "val" or n_seen == 0:
+                break
+        self.last_iter = it - 1
+        self.model.check_status()
+
+    def display(self):
+        """nerf.py:503-530: no-grad render of every test batch, scattered into (num_pic, H, W, 3)."""
+        result = torch.full((self.num_pic, self.height, self.width, 3), 1.0, device=device)
+        with torch.no_grad():
+            self.model.eval()
+            for (row, column, pix_val, poses_bound, pic) in self.disp_dataloader:
+                _, c_fine = self.model(row, column, poses_bound, self.K_inv)
+                result[pic.to(device), row.to(device), column.to(device)] = c_fine
+        return result

@@ -172,14 +172,21 @@ def freq_from_hex(table) -> np.ndarray:
     return np.array(table, dtype=np.uint32).view(f32)
 
 
-def encode(x: torch.Tensor, L: int) -> torch.Tensor:
+def encode(x: torch.Tensor, L: int, faithful32: bool = False) -> torch.Tensor:
     """nerf.py:135-167 + flatten at nerf.py:103-104: feature index c*2L + 2l + s,
-    argument fl(w_l * x_c).  x [...,3] -> [...,6L]."""
+    argument fl(w_l * x_c).  x [...,3] -> [...,6L].
+    faithful32 (fp64 inputs only): the sin/cos ARGUMENT takes the value the fp32 path computes
+    (fl32(w32 * fl32(x))) while autograd still differentiates the fp64 expression — the fp64
+    gradient oracle for kernels that consume fp32 positions."""
     if x.dtype == torch.float32:
         w = torch.from_numpy(freq_from_hex(FREQ_POINT_HEX if L == 10 else FREQ_DIR_HEX))
     else:  # fp64 oracle (SURVEY.md §4.1): the reference then evaluates nerf.py:141-145 in double
         w = torch.exp2(torch.linspace(0, L, L, dtype=x.dtype)) * math.pi
     arg = x.unsqueeze(-1) * w  # [...,3,L]
+    if faithful32 and x.dtype == torch.float64:
+        w32 = torch.from_numpy(freq_from_hex(FREQ_POINT_HEX if L == 10 else FREQ_DIR_HEX))
+        arg32 = (x.detach().float().unsqueeze(-1) * w32).double()
+        arg = arg + (arg32 - arg).detach()
     out = torch.stack((torch.sin(arg), torch.cos(arg)), dim=-1)  # [...,3,L,2]
     return out.flatten(start_dim=-3)
 
@@ -267,7 +274,8 @@ def merge_sort_composite(t_c, color_c, sigma_c, t_f, color_f, sigma_f, last: flo
 # ---------------------------------------------------------------------------
 # a13: full forward (nerf.py:286-348)
 # ---------------------------------------------------------------------------
-def net_out(sd, t: torch.Tensor, d_cam: np.ndarray, d_wrd: np.ndarray, c2w: np.ndarray, t_requires_path: bool = False):
+def net_out(sd, t: torch.Tensor, d_cam: np.ndarray, d_wrd: np.ndarray, c2w: np.ndarray, t_requires_path: bool = False,
+            faithful32: bool = False):
     """nerf.py:179-222 for a [N,P] array of t.  If ``t`` carries grad the sample
     positions are rebuilt in torch (p = R*(d_cam*t)+T) so autograd reaches t."""
     n, p = t.shape
@@ -283,8 +291,11 @@ def net_out(sd, t: torch.Tensor, d_cam: np.ndarray, d_wrd: np.ndarray, c2w: np.n
         acc = acc + c[:, None, r, 2] * pc[:, :, 2]
         cols.append(acc + c[:, None, r, 3])
     pts = torch.stack(cols, dim=-1)
+    if faithful32 and dt == torch.float64:   # positions take their fp32 values, gradients stay fp64
+        p32 = sample_points(d_cam.astype(f32), t.detach().float().numpy(), np.asarray(c2w, dtype=f32))
+        pts = pts + (torch.from_numpy(p32).double() - pts).detach()
     dirs = torch.from_numpy(d_wrd).to(dt)[:, None, :].expand(n, p, 3)
-    color, sigma = network_forward(sd, encode(pts, 10), encode(dirs, 4))
+    color, sigma = network_forward(sd, encode(pts, 10, faithful32), encode(dirs, 4, faithful32))
     return color, sigma.squeeze(-1)
 
 

@@ -1,0 +1,336 @@
+"""GPU parity: every CUDA kernel, called through the C-ABI, against the oracle and the reference-made goldens.
+
+Bit-exact (north_star): ray directions, coarse sample positions, searchsorted indices, t_fine given identical
+inputs.  Tolerances: rgb within 1e-3 max-abs in fp32 mode, 1e-2 in bf16 mode (written next to each assert).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["kat8", "lego48", "lego48_trained", "fern64", "fern64_trained"]
+FP32, BF16 = 0, 2
+
+
+def bits(a):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32)).view(np.uint32)
+
+
+def sd_of(case):
+    sd = O.init_state_dict(624)
+    return O.trained_like(sd) if case.endswith("trained") else sd
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from nerf_tiny_b200 import build, ops
+    build.build()
+    c = ops.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def load(golden_dir, case):
+    return np.load(os.path.join(golden_dir, case + ".npz"))
+
+
+def cu(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t.to(dtype) if dtype is not None else t
+
+
+def flat_of(sd, dev):
+    from nerf_tiny_b200.ops import flatten_state_dict
+    return flatten_state_dict(sd, dev)
+
+
+# ------------------------------------------------------------------------------------------------ geometry
+@pytest.mark.parametrize("case", CASES)
+def test_raygen_bit_exact(ctx, dev, golden_dir, case):
+    g = load(golden_dir, case)
+    rays, dw, de = ctx.raygen(cu(g["row"], dev), cu(g["col"], dev), cu(g["c2w"], dev), cu(g["k_inv"], dev))
+    assert np.array_equal(bits(rays[:, :3]), bits(g["d_cam"]))
+    assert np.array_equal(bits(dw), bits(g["d_wrd"]))
+    ref_enc = O.encode(torch.from_numpy(g["d_wrd"]), 4).numpy()
+    assert np.abs(de.cpu().numpy() - ref_enc).max() <= 2e-7       # sincosf vs torch CPU sin/cos
+    # the loader's 17-vector layout gives the same bits
+    pb = cu(g["poses_bound"].astype(np.float32), dev)
+    rays2, dw2, _ = ctx.raygen(cu(g["row"], dev), cu(g["col"], dev), pb, cu(g["k_inv"], dev))
+    assert torch.equal(rays, rays2) and torch.equal(dw, dw2)
+
+
+@pytest.mark.parametrize("hw", [(400, 400, 555.6), (378, 504, 407.6), (800, 800, 1111.1)])
+def test_raygen_full_view_bit_exact(ctx, dev, hw):
+    """BASELINE configs' full image sizes: every pixel of a view, bit-for-bit against the oracle."""
+    from nerf_tiny_b200 import synth
+    h, w, f = hw
+    rows17 = synth.pose_rows(3, h, w, f, llff_bounds=True, seed=1)
+    row, col, _, pb, _ = synth.view_batch(rows17, 1, h, w)
+    kinv = synth.k_inv_of(h, w, f)
+    pbf = pb.to(torch.float32)
+    c2w = O.poses_extract(pbf)[0].numpy()
+    d_cam, d_wrd = O.ray_dirs(row.numpy(), col.numpy(), kinv.numpy(), c2w)
+    rays, dw, _ = ctx.raygen(row.to(dev), col.to(dev), pbf.to(dev), kinv.to(dev))
+    assert np.array_equal(bits(rays[:, :3]), bits(d_cam))
+    assert np.array_equal(bits(dw), bits(d_wrd))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_t_coarse_bit_exact(ctx, dev, golden_dir, case):
+    g = load(golden_dir, case)
+    t = ctx.sample_coarse(cu(g["near"], dev), cu(g["far"], dev))
+    assert np.array_equal(bits(t), bits(g["t_coarse"]))
+
+
+def test_t_coarse_random_and_step_zero(ctx, dev):
+    rng = np.random.RandomState(0)
+    near = rng.uniform(0.5, 3, 4099).astype(np.float32)
+    far = (near + rng.uniform(0.1, 12, 4099)).astype(np.float32)
+    t = ctx.sample_coarse(cu(near, dev), cu(far, dev))
+    assert np.array_equal(bits(t), bits(O.t_coarse_of(near, far)))
+    # one degenerate ray flips EVERY ray to numpy's any_step_zero formula
+    far[77] = near[77]
+    t = ctx.sample_coarse(cu(near, dev), cu(far, dev))
+    assert np.array_equal(bits(t), bits(O.t_coarse_of(near, far)))
+    # a shard that does not contain the degenerate ray is told the global flag
+    t = ctx.sample_coarse(cu(near[:64], dev), cu(far[:64], dev), any_step_zero=1)
+    assert np.array_equal(bits(t), bits(O.t_coarse_of(near, far)[:64]))
+    assert ctx.sample_coarse(cu(near[:0], dev), cu(far[:0], dev)).shape == (0, 64)      # empty input
+
+
+# ------------------------------------------------------------------------------------------------ resampling
+@pytest.mark.parametrize("case", CASES)
+def test_sample_pdf_bit_exact(ctx, dev, golden_dir, case):
+    g = load(golden_dir, case)
+    t_f, idx = ctx.sample_pdf(cu(g["t_coarse"], dev), cu(g["w_c"], dev))
+    ctx.check_status()
+    assert np.array_equal(idx.cpu().numpy(), g["idx"])
+    assert np.array_equal(bits(t_f), bits(g["t_fine"]))
+
+
+def test_sample_pdf_random_large(ctx, dev):
+    rng = np.random.RandomState(3)
+    n = 20000
+    near = rng.uniform(1, 2, n).astype(np.float32)
+    far = (near + rng.uniform(2, 10, n)).astype(np.float32)
+    t_c = O.t_coarse_of(near, far)
+    # peaky weights incl. exact zeros (ties in the cdf)
+    w = (rng.rand(n, 64) ** 8).astype(np.float32)
+    w[rng.rand(n, 64) < 0.2] = 0.0
+    w[:, 1] += 1e-3
+    t_ref, idx_ref, _, _ = O.resample(torch.from_numpy(t_c), torch.from_numpy(w), return_aux=True)
+    t_f, idx = ctx.sample_pdf(cu(t_c, dev), cu(w, dev))
+    ctx.check_status()
+    assert np.array_equal(idx.cpu().numpy(), idx_ref.numpy().astype(np.int32))
+    assert np.array_equal(bits(t_f), bits(t_ref.numpy()))
+
+
+def test_sample_pdf_range_error(ctx, dev):
+    from nerf_tiny_b200 import _lib
+    t_c = O.t_coarse_of(np.array([2.0, 2.0], np.float32), np.array([6.0, 6.0], np.float32))
+    w = np.zeros((2, 64), np.float32)
+    w[1] = 0.01
+    ctx.sample_pdf(cu(t_c, dev), cu(w, dev))
+    with pytest.raises(_lib.ResampleRangeError):      # the reference exit(0)s here (nerf.py:251-253)
+        ctx.check_status()
+    ctx.check_status()                                 # flag cleared
+
+
+def test_sample_pdf_backward(ctx, dev, golden_dir):
+    g = load(golden_dir, "fern64_trained")
+    w = torch.from_numpy(g["w_c"]).double().requires_grad_(True)
+    t_c = torch.from_numpy(g["t_coarse"]).double()
+    # fp64 autograd through the oracle with u/idx fixed to the fp32 forward's values
+    t_f = O.resample(t_c, w)
+    gt = torch.randn(t_f.shape, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+    (t_f * gt).sum().backward()
+    g_w = ctx.sample_pdf_backward(cu(g["t_coarse"], dev), cu(g["w_c"], dev), cu(gt.float().numpy(), dev))
+    ref = w.grad.numpy()
+    err = np.abs(g_w.cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err < 1e-3, err          # fp32 kernel vs fp64 autograd; 1/(w+eps)^2 terms amplify rounding
+
+
+# ------------------------------------------------------------------------------------------------ compositing
+@pytest.mark.parametrize("case", CASES)
+def test_composite_coarse(ctx, dev, golden_dir, case):
+    g = load(golden_dir, case)
+    w, c = ctx.composite_coarse(cu(g["near"], dev), cu(g["far"], dev), cu(g["color_c"], dev), cu(g["sigma_c"], dev))
+    assert np.abs(w.cpu().numpy() - g["w_c"]).max() <= 1e-6       # expf vs torch CPU exp
+    assert np.abs(c.cpu().numpy() - g["c_coarse"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_composite_fine(ctx, dev, golden_dir, case):
+    g = load(golden_dir, case)
+    args = [cu(g[k], dev) for k in ("t_coarse", "color_c", "sigma_c", "t_fine", "color_f", "sigma_f")]
+    c, w, perm = ctx.composite_fine(*args)
+    assert np.abs(c.cpu().numpy() - g["c_fine"]).max() <= 1e-5
+    T = lambda k: torch.from_numpy(g[k])
+    _, w_ref, t_s, col_s, sig_s = O.merge_sort_composite(T("t_coarse"), T("color_c"), T("sigma_c"), T("t_fine"), T("color_f"),
+                                                         T("sigma_f"))
+    assert np.abs(w.cpu().numpy() - w_ref.numpy()).max() <= 1e-6
+    # the permutations reproduce each independently sorted channel bit-for-bit
+    perm = perm.cpu().numpy().astype(np.int64)
+    t_all = np.concatenate((g["t_coarse"], g["t_fine"]), axis=1)
+    assert np.array_equal(np.take_along_axis(t_all, perm[:, 0], 1), t_s.numpy())
+    sig_all = np.concatenate((g["sigma_c"], g["sigma_f"]), axis=1)
+    assert np.array_equal(np.take_along_axis(sig_all, perm[:, 4], 1), sig_s.numpy())
+    col_all = np.concatenate((g["color_c"], g["color_f"]), axis=1)
+    for ch in range(3):
+        assert np.array_equal(np.take_along_axis(col_all[:, :, ch], perm[:, 1 + ch], 1), col_s[:, :, ch].numpy())
+    for ch in range(5):
+        assert np.array_equal(np.sort(perm[:, ch], axis=1), np.tile(np.arange(192), (perm.shape[0], 1)))
+
+
+def test_composite_backward(ctx, dev, golden_dir):
+    g = load(golden_dir, "fern64_trained")
+    T = lambda k: torch.from_numpy(g[k]).double()
+    gen = torch.Generator().manual_seed(1)
+    # coarse
+    near, far = T("near"), T("far")
+    rgb = T("color_c").requires_grad_(True)
+    sig = T("sigma_c").requires_grad_(True)
+    delta = ((far - near) / 64)[:, None].expand(-1, 64)
+    w = O.get_density(delta, sig)
+    gc = torch.randn(rgb.shape[0], 3, generator=gen, dtype=torch.float64)
+    gw = torch.randn(w.shape, generator=gen, dtype=torch.float64)
+    ((O.color_cum(w, rgb) * gc).sum() + (w * gw).sum()).backward()
+    g_rgb, g_sig = ctx.composite_coarse_backward(cu(g["near"], dev), cu(g["far"], dev), cu(g["color_c"], dev), cu(g["sigma_c"], dev),
+                                                 cu(gc.float().numpy(), dev), cu(gw.float().numpy(), dev))
+    assert np.abs(g_rgb.cpu().numpy() - rgb.grad.numpy()).max() <= 1e-5 * max(1, rgb.grad.abs().max())
+    assert np.abs(g_sig.cpu().numpy() - sig.grad.numpy()).max() <= 2e-5 * max(1, sig.grad.abs().max())
+    # fine (through the 5 independent sorts)
+    leaves = {k: T(k).requires_grad_(k != "t_coarse") for k in ("t_coarse", "color_c", "sigma_c", "t_fine", "color_f", "sigma_f")}
+    c_fine = O.merge_sort_composite(*leaves.values())[0]
+    (c_fine * gc).sum().backward()
+    args = [cu(g[k], dev) for k in leaves]
+    _, _, perm = ctx.composite_fine(*args)
+    outs = ctx.composite_fine_backward(*args, perm, cu(gc.float().numpy(), dev))
+    for got, k in zip(outs, ("color_c", "sigma_c", "color_f", "sigma_f", "t_fine")):
+        ref = leaves[k].grad.numpy()
+        err = np.abs(got.cpu().numpy() - ref).max() / max(1e-12, np.abs(ref).max())
+        assert err < 5e-5, (k, err)
+
+
+# ------------------------------------------------------------------------------------------------ MLP
+@pytest.mark.parametrize("case", CASES)
+def test_mlp_fp32_forward(ctx, dev, golden_dir, case):
+    g = load(golden_dir, case)
+    flat = flat_of(sd_of(case), dev)
+    rays, _, de = ctx.raygen(cu(g["row"], dev), cu(g["col"], dev), cu(g["c2w"], dev), cu(g["k_inv"], dev))
+    for tk, ck, sk in (("t_coarse", "color_c", "sigma_c"), ("t_fine", "color_f", "sigma_f")):
+        rgb, sigma, _ = ctx.mlp_forward(FP32, cu(g[tk], dev), rays, de, flat)
+        assert np.abs(rgb.cpu().numpy() - g[ck]).max() <= 2e-5, (tk, "rgb")      # fp32 mode budget is 1e-3
+        s_ref = g[sk]
+        assert np.abs(sigma.cpu().numpy() - s_ref).max() <= 2e-5 * max(1.0, np.abs(s_ref).max()), (tk, "sigma")
+
+
+def test_mlp_fp32_backward(ctx, dev, golden_dir):
+    g = load(golden_dir, "kat8")
+    sd32 = sd_of("kat8_trained")
+    flat = flat_of(sd32, dev)
+    rays, _, de = ctx.raygen(cu(g["row"], dev), cu(g["col"], dev), cu(g["c2w"], dev), cu(g["k_inv"], dev))
+    t = cu(g["t_fine"], dev)
+    rgb, sigma, ws = ctx.mlp_forward(FP32, t, rays, de, flat, train=True)
+    gen = torch.Generator().manual_seed(4)
+    g_rgb = torch.randn(rgb.shape, generator=gen)
+    g_sig = torch.randn(sigma.shape, generator=gen) * 0.01
+    grads, g_t = ctx.mlp_backward(FP32, t, rays, de, flat, None, g_rgb.to(dev), g_sig.to(dev), ws)
+    # fp64 oracle autograd on identical inputs
+    sd = {k: v.double().requires_grad_(True) for k, v in sd32.items()}
+    tt = torch.from_numpy(g["t_fine"]).double().requires_grad_(True)
+    d_cam, d_wrd = O.ray_dirs(g["row"], g["col"], g["k_inv"], g["c2w"])
+    d_cam, d_wrd = d_cam.astype(np.float64), d_wrd.astype(np.float64)
+    color, sig = O.net_out(sd, tt, d_cam, d_wrd, g["c2w"].astype(np.float64), faithful32=True)
+    ((color * g_rgb.double()).sum() + (sig * g_sig.double()).sum()).backward()
+    from nerf_tiny_b200 import _lib
+    gflat = grads.cpu().numpy()
+    rels = {}
+    for (o, i, wo, bo), key in zip(_lib.layer_table(), O.LAYER_KEYS):
+        for off, n, name in ((wo, o * i, ".weight"), (bo, o, ".bias")):
+            ref = sd[key + name].grad.numpy().reshape(-1)
+            got = gflat[off:off + n]
+            rels[key + name] = np.linalg.norm(got - ref) / max(1e-20, np.linalg.norm(ref))
+    ref_t = tt.grad.numpy()
+    rels["g_t"] = np.linalg.norm(g_t.cpu().numpy() - ref_t) / np.linalg.norm(ref_t)
+    print({k: float("%.2e" % v) for k, v in rels.items()})
+    bad = {k: v for k, v in rels.items() if v > (2e-3 if k != "g_t" else 2e-2)}
+    assert not bad, bad      # g_t: d enc / dt carries w_l up to 3217 with cancellation
+
+
+# ------------------------------------------------------------------------------------------------ end to end
+def model_of(case, dev, precision):
+    from nerf_tiny_b200 import nerf
+    m = nerf.NeRFModel(64, 128, batch_ray=8, precision=precision)
+    m.load_state_dict(sd_of(case))
+    return m.to(dev)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_forward_fp32_matches_reference(dev, golden_dir, case):
+    g = load(golden_dir, case)
+    m = model_of(case, dev, "fp32")
+    with torch.no_grad():
+        cc, cf = m(torch.from_numpy(g["row"]), torch.from_numpy(g["col"]), torch.from_numpy(g["poses_bound"]),
+                   torch.from_numpy(g["k_inv"]))
+    assert np.abs(cc.cpu().numpy() - g["c_coarse"]).max() <= 1e-3      # north_star fp32 tolerance
+    assert np.abs(cf.cpu().numpy() - g["c_fine"]).max() <= 1e-3
+    assert np.abs(cc.cpu().numpy() - g["c_coarse"]).max() <= 5e-5      # what we actually hold
+    assert m.launch_count > 0
+
+
+def test_state_dict_keys_match_reference(dev):
+    from nerf_tiny_b200 import nerf
+    m = nerf.NeRFModel(64, 128, batch_ray=8)
+    sd = O.init_state_dict(624)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    assert sum(p.numel() for p in m.network.parameters()) == 593924
+
+
+def test_adam_matches_golden(ctx, dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "adam5.npz"))
+    n = 1000
+    p = cu(g["p0"], dev).clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for s, gr in enumerate(g["grads"], 1):
+        ctx.adam_step(p, cu(gr, dev), m, v, 3e-4, s)
+    assert np.abs(p.cpu().numpy() - g["p_final"]).max() < 1e-6
+
+
+def test_autograd_and_train_step_agree(dev, golden_dir):
+    """loss.backward() through the drop-in == the fused train_step's gradient; both against the fp64 oracle loss."""
+    from nerf_tiny_b200 import nerf
+    g = load(golden_dir, "kat8")
+    m = model_of("kat8", dev, "fp32")
+    row, col = torch.from_numpy(g["row"]), torch.from_numpy(g["col"])
+    pb, kinv = torch.from_numpy(g["poses_bound"]), torch.from_numpy(g["k_inv"])
+    tgt = torch.full((8, 3), 0.5)
+    m.train()
+    cc, cf = m(row, col, pb, kinv)
+    loss = m.ray_loss(cc, cf, tgt)
+    m.network.flat_grads().zero_()
+    loss.backward()
+    g_auto = m.network.flat_grads().clone()
+    with torch.no_grad():
+        occ, ocf = O.forward(sd_of("kat8"), g["row"], g["col"], pb, kinv)
+        ref_loss = float(O.ray_loss(occ, ocf, tgt))
+    assert abs(float(loss) - ref_loss) < 1e-4 * ref_loss
+    opt = nerf.FusedAdam(m, lr=0.0)
+    loss2, _, _ = nerf.train_step(m, opt, row, col, tgt, pb, kinv)
+    g_fused = m.network.flat_grads()
+    assert abs(float(loss2) - ref_loss) < 1e-4 * ref_loss
+    rel = float((g_auto - g_fused).norm() / g_fused.norm())
+    assert rel < 1e-5, rel
+    assert float(g_fused.norm()) > 0
