@@ -99,6 +99,12 @@ int nt_mlp_backward(nt_ctx* ctx, int precision, int64_t n, int p, const float* t
                     const float* dir_enc, const float* params, const void* packed, const float* g_rgb,
                     const float* g_sigma, float* grads, float* g_t, void* ws, size_t ws_bytes, void* stream);
 
+/* Diagnostic (NT_PREC_BF16): as nt_mlp_forward, and dumps the fp32 post-activation output of one tensor-core
+ * layer (0..7 trunk nerf.py:85-91, 8 point_info :96, 9 dir_info :98) to dbg dev [N*P,256]. */
+int nt_mlp_forward_debug(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                         const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int layer,
+                         void* stream);
+
 /* ---- compositing: get_density nerf.py:263-272 + color_cum nerf.py:274-281 ----------------
  * coarse: delta = (far-near)/Nc for every sample (nerf.py:293).  weights dev [N,Nc], c_out dev [N,3]. */
 int nt_composite_coarse(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, const float* rgb,

@@ -254,3 +254,13 @@ static int nt_launch_axpy(nt_ctx* ctx, int64_t n, const float* x, float* y, cuda
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;
 }
+
+// diagnostic: NT_PREC_BF16 forward that also dumps one MMA layer's post-activation fp32 output (dbg dev [N*P,256];
+// layer 0..7 = trunk, 8 = point_info, 9 = dir_info) — used by the layer-by-layer parity test
+extern "C" int nt_mlp_forward_debug(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays,
+                                    const float* dir_enc, const float* params, const void* packed, float* rgb,
+                                    float* sigma, float* dbg, int layer, void* stream) {
+  NT_REQUIRE(ctx && t && rays && dir_enc && params && packed && rgb && sigma && dbg, "null pointer");
+  if (n <= 0) return NT_OK;
+  return nt_mlp_tc_forward_dbg(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, dbg, layer, (cudaStream_t)stream);
+}

@@ -120,3 +120,6 @@ size_t nt_mlp_tc_packed_bytes();
 int nt_mlp_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t st);
 int nt_mlp_tc_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                       const float* params, const void* packed, float* rgb, float* sigma, cudaStream_t st);
+int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                          const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int dbg_layer,
+                          cudaStream_t st);

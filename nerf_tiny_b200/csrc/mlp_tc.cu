@@ -1,5 +1,515 @@
-// placeholder, replaced by the tcgen05 kernel
+// NT_PREC_BF16: fused positional-encoding + 8x256 MLP forward on the 5th-gen tensor cores (sm_100a).
+// Reference: net_out nerf.py:200-219 -> Encoder.forward nerf.py:135-167 -> Network.forward nerf.py:101-124.
+//
+// One persistent CTA per SM works on PAIRS of 128-sample tiles (A, B):
+//   * sin/cos features are generated in registers by the tile's 4 epilogue warps and stored as bf16 straight into
+//     the 128B-swizzled K-major A-operand layout in shared memory (never touch HBM);
+//   * every layer's bf16 weights are pre-packed (nt_pack_weights) as ready-to-use swizzled [N x 64] K-chunks and
+//     streamed by a TMA bulk-copy producer warp through a 2-stage shared-memory ring; each chunk is consumed by
+//     BOTH tiles before it is released (weights cross L2->SMEM once per 256 samples);
+//   * one elected thread issues tcgen05.mma (M=128, N=256|128, K=16, bf16 -> fp32) accumulating in TMEM
+//     (tile A: columns 0-255, tile B: 256-511);
+//   * the epilogue warps read the accumulator with tcgen05.ld, add bias, apply ReLU, round to bf16 and write the
+//     next layer's A operand in place; the sigma head (256->1, abs) and colour head (128->3, sigmoid) are evaluated
+//     on CUDA cores from the fp32 accumulators in the same pass.
+// Skip (nerf.py:109) and view (nerf.py:118) concatenations are extra K-chunks accumulated into the same TMEM tile.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
-size_t nt_mlp_tc_packed_bytes() { return 256; }
-int nt_mlp_tc_pack(nt_ctx*, const float*, void*, cudaStream_t) { nt_set_error("bf16 path not built"); return NT_ERR_UNSUPPORTED; }
-int nt_mlp_tc_forward(nt_ctx*, int64_t, int, const float*, const float*, const float*, const float*, const void*, float*, float*, cudaStream_t) { nt_set_error("bf16 path not built"); return NT_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int CHUNK_A_BYTES = TILE_M * 128;      // [128 rows x 64 bf16], one swizzle row per sample
+constexpr int ACT_BYTES = 4 * CHUNK_A_BYTES;     // 256-wide activations
+constexpr int W_STAGE_BYTES = 256 * 128;         // [256 x 64] bf16
+constexpr int N_STAGES = 2;
+constexpr int OFF_ACT = 0;
+constexpr int OFF_ENC = 2 * ACT_BYTES;
+constexpr int OFF_W = OFF_ENC + 2 * CHUNK_A_BYTES;
+constexpr int OFF_BAR = OFF_W + N_STAGES * W_STAGE_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int N_MMA_LAYERS = 10;  // L0..L7, point_info, dir_info
+constexpr int N_THREADS = 320;    // 8 epilogue warps + TMA producer + MMA issuer
+
+// barrier slots (8 B each) inside the OFF_BAR block
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 2, BAR_ACC_FULL = 4, BAR_ACT_READY = 6, BAR_COUNT = 8 };
+
+__host__ __device__ constexpr int layer_chunks(int L) { return L == 0 ? 1 : ((L == 4 || L == 9) ? 5 : 4); }
+__host__ __device__ constexpr int layer_n(int L) { return L == 9 ? 128 : 256; }
+__host__ __device__ constexpr int chunk_bytes(int L) { return layer_n(L) * 128; }
+constexpr int total_packed_bytes() {
+  int b = 0;
+  for (int L = 0; L < N_MMA_LAYERS; ++L) b += layer_chunks(L) * chunk_bytes(L);
+  return b;
+}
+constexpr int PACKED_W_BYTES = total_packed_bytes();  // 1 196 032
+// fp32 side block appended to the packed weights, 16-byte aligned (the flat parameter buffer is not: the
+// 1-wide sigma bias shifts everything after it by one float)
+constexpr int AUX_BIAS = 0;            // 10 x 256
+constexpr int AUX_SIG_W = 2560;        // 256
+constexpr int AUX_COL_W = 2816;        // 3 x 128
+constexpr int AUX_SIG_B = 3200;
+constexpr int AUX_COL_B = 3201;        // 3
+constexpr int AUX_FLOATS = 3208;
+constexpr int PACKED_BYTES = PACKED_W_BYTES + AUX_FLOATS * 4;
+
+struct TcParams {
+  const float* t;
+  const float* rays;
+  const float* dir_enc;
+  const float* params;
+  const uint8_t* packed;
+  float* rgb;
+  float* sigma;
+  float* dbg;  // optional [S,256] fp32 dump of one layer's post-activation output
+  int dbg_layer;
+  int64_t total;  // samples
+  int p;          // samples per ray
+  int num_pairs;
+};
+
+__constant__ uint32_t c_tc_freq_point[10] = NT_FREQ_POINT_INIT;
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins == 1024) t0 = clock64();
+    if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();  // ~2 s: never hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc_512(uint32_t smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_slot) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+
+// SM100 shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo -> lower address
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// A-operand row `row`, 16-byte chunk `j` (0..7) of a [128 x 64] bf16 SW128 tile at `tile`
+__device__ __forceinline__ uint32_t a_chunk_addr(uint32_t tile, int row, int j) {
+  return tile + row * 128 + ((j ^ (row & 7)) << 4);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = sbase + OFF_BAR;
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023) __trap();  // SWIZZLE_128B operands need a 1024-byte aligned base
+    for (int s = 0; s < N_STAGES; ++s) {
+      mbar_init(bar(BAR_W_FULL + s), 1);
+      mbar_init(bar(BAR_W_EMPTY + s), 1);
+    }
+    for (int tl = 0; tl < 2; ++tl) {
+      mbar_init(bar(BAR_ACC_FULL + tl), 1);
+      mbar_init(bar(BAR_ACT_READY + tl), TILE_M);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc_512(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== TMA producer: weight K-chunks, same order for every tile pair =====================
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
+        const uint8_t* src = P.packed;
+        for (int L = 0; L < N_MMA_LAYERS; ++L) {
+          const uint32_t bytes = chunk_bytes(L);
+          for (int kc = 0; kc < layer_chunks(L); ++kc, ++q) {
+            const uint32_t stage = q & 1;
+            mbar_wait(bar(BAR_W_EMPTY + stage), ((q >> 1) & 1) ^ 1);
+            mbar_expect_tx(bar(BAR_W_FULL + stage), bytes);
+            tma_bulk_g2s(sbase + OFF_W + stage * W_STAGE_BYTES, src, bytes, bar(BAR_W_FULL + stage));
+            src += bytes;
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer: one thread drives the tensor core for both tiles =====================
+    if (lane == 0) {
+      uint32_t q = 0, lit = 0;
+      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
+        for (int L = 0; L < N_MMA_LAYERS; ++L, ++lit) {
+          const int nch = layer_chunks(L);
+          const uint32_t idesc = umma_idesc(layer_n(L));
+          for (int kc = 0; kc < nch; ++kc, ++q) {
+            const uint32_t stage = q & 1;
+            mbar_wait(bar(BAR_W_FULL + stage), (q >> 1) & 1);
+            tc_fence_after();
+            const uint32_t b_addr = sbase + OFF_W + stage * W_STAGE_BYTES;
+#pragma unroll
+            for (int tl = 0; tl < 2; ++tl) {
+              if (kc == 0) {  // A operand written + accumulator drained by the tile's epilogue warps
+                mbar_wait(bar(BAR_ACT_READY + tl), lit & 1);
+                tc_fence_after();
+              }
+              const bool from_enc = (L == 0) || (kc == 4);
+              const uint32_t a_addr = from_enc ? sbase + OFF_ENC + tl * CHUNK_A_BYTES
+                                               : sbase + OFF_ACT + tl * ACT_BYTES + kc * CHUNK_A_BYTES;
+              const uint32_t d_tmem = tmem_base + tl * 256;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)  // 4 x (K = 16) inside the 64-wide swizzled chunk: +32 B per step
+                umma_bf16(d_tmem, umma_desc(a_addr + j * 32), umma_desc(b_addr + j * 32), idesc, (kc | j) != 0);
+              if (kc == nch - 1) umma_commit(bar(BAR_ACC_FULL + tl));
+            }
+            umma_commit(bar(BAR_W_EMPTY + stage));  // frees the ring slot once both tiles' MMAs retire
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== encode + epilogue warps: 4 per tile, one sample (TMEM lane) per thread ===========
+    const int tl = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
+    const uint32_t enc = sbase + OFF_ENC + tl * CHUNK_A_BYTES;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + tl * 256;
+    const float* __restrict__ aux = reinterpret_cast<const float*>(P.packed + PACKED_W_BYTES);
+    uint32_t it = 0;
+    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
+      const int64_t s = ((int64_t)pair * 2 + tl) * TILE_M + row;
+      const bool valid = s < P.total;
+      const int64_t sc = valid ? s : P.total - 1;
+      const int64_t ray = sc / P.p;
+      // ---- positional encoding of this sample (nerf.py:200-216, 135-167) -> enc tile, bf16, swizzled ----
+      {
+        const float4* rp = reinterpret_cast<const float4*>(P.rays + ray * 16);
+        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+        const float tt = __ldg(P.t + sc);
+        const float pc0 = __fmul_rn(r0.x, tt), pc1 = __fmul_rn(r0.y, tt), pc2 = __fmul_rn(r0.z, tt);
+        float pos[3];
+        pos[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.w, pc0), __fmul_rn(r1.x, pc1)), __fmul_rn(r1.y, pc2)), r3.x);
+        pos[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.z, pc0), __fmul_rn(r1.w, pc1)), __fmul_rn(r2.x, pc2)), r3.y);
+        pos[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.y, pc0), __fmul_rn(r2.z, pc1)), __fmul_rn(r2.w, pc2)), r3.z);
+        uint32_t f[32];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int l = 0; l < 10; ++l) {
+            float sn, cs;
+            sincosf(__fmul_rn(__uint_as_float(c_tc_freq_point[l]), pos[c]), &sn, &cs);
+            f[c * 10 + l] = pack_bf16(sn, cs);  // features (c*20+2l, c*20+2l+1)
+          }
+        f[30] = 0u;
+        f[31] = 0u;  // K padded 60 -> 64
+#pragma unroll
+        for (int j = 0; j < 8; ++j) st_shared_v4(a_chunk_addr(enc, row, j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar(BAR_ACT_READY + tl));
+
+      for (int L = 0; L < N_MMA_LAYERS; ++L, ++it) {
+        mbar_wait(bar(BAR_ACC_FULL + tl), it & 1);
+        tc_fence_after();
+        const float* __restrict__ bias = aux + AUX_BIAS + L * 256;
+        const int ncb = layer_n(L) / 32;
+        float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        for (int cb = 0; cb < ncb; ++cb) {
+          float v[32];
+          tmem_ld32(tmem_row + cb * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cb * 32 + j));
+            v[j] += b4.x;
+            v[j + 1] += b4.y;
+            v[j + 2] += b4.z;
+            v[j + 3] += b4.w;
+          }
+          if (L != 8) {  // point_info has no activation (nerf.py:117)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (P.dbg && P.dbg_layer == L && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) P.dbg[s * 256 + cb * 32 + j] = v[j];
+          }
+          if (L == 7) {  // sigma head from the fp32 activations (nerf.py:94, :114)
+            const float* __restrict__ ws = aux + AUX_SIG_W + cb * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(ws + j));
+              sig_acc = fmaf(v[j], w4.x, sig_acc);
+              sig_acc = fmaf(v[j + 1], w4.y, sig_acc);
+              sig_acc = fmaf(v[j + 2], w4.z, sig_acc);
+              sig_acc = fmaf(v[j + 3], w4.w, sig_acc);
+            }
+          }
+          if (L == 9) {  // colour head (nerf.py:99, :119)
+            const float* __restrict__ wc = aux + AUX_COL_W + cb * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              c0 = fmaf(v[j], __ldg(wc + j), c0);
+              c1 = fmaf(v[j], __ldg(wc + 128 + j), c1);
+              c2 = fmaf(v[j], __ldg(wc + 256 + j), c2);
+            }
+          } else {  // next layer's A operand: K-chunk cb/2, 16-byte chunks (cb%2)*4 .. +3
+            const uint32_t dst = act + (cb >> 1) * CHUNK_A_BYTES;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd)
+              st_shared_v4(a_chunk_addr(dst, row, (cb & 1) * 4 + qd), pack_bf16(v[8 * qd], v[8 * qd + 1]),
+                           pack_bf16(v[8 * qd + 2], v[8 * qd + 3]), pack_bf16(v[8 * qd + 4], v[8 * qd + 5]),
+                           pack_bf16(v[8 * qd + 6], v[8 * qd + 7]));
+          }
+        }
+        if (L == 4) {
+          // all MMAs that read the xyz features have retired: reuse the tile for the view-direction features
+          const float4* de = reinterpret_cast<const float4*>(P.dir_enc + ray * 24);
+          uint32_t f[12];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const float4 d4 = __ldg(de + j);
+            f[2 * j] = pack_bf16(d4.x, d4.y);
+            f[2 * j + 1] = pack_bf16(d4.z, d4.w);
+          }
+#pragma unroll
+          for (int j = 0; j < 3; ++j) st_shared_v4(a_chunk_addr(enc, row, j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+#pragma unroll
+          for (int j = 3; j < 8; ++j) st_shared_v4(a_chunk_addr(enc, row, j), 0u, 0u, 0u, 0u);
+        }
+        if (L == 7 && valid) P.sigma[s] = fabsf(sig_acc + __ldg(aux + AUX_SIG_B));
+        if (L == 9) {
+          if (valid) {
+            P.rgb[s * 3 + 0] = 1.f / (1.f + __expf(-(c0 + __ldg(aux + AUX_COL_B))));
+            P.rgb[s * 3 + 1] = 1.f / (1.f + __expf(-(c1 + __ldg(aux + AUX_COL_B + 1))));
+            P.rgb[s * 3 + 2] = 1.f / (1.f + __expf(-(c2 + __ldg(aux + AUX_COL_B + 2))));
+          }
+        } else {
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          tc_fence_before();
+          mbar_arrive(bar(BAR_ACT_READY + tl));
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc_512(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight packing: nn.Linear (out,in) fp32 -> bf16 [N x 64] SW128 K-chunks in consumption order
+// ---------------------------------------------------------------------------------------------------------
+struct PackLayer {
+  int w_off, ld, n;  // flat weight offset, row length (in_features), rows
+};
+struct PackParams {
+  PackLayer layer[N_MMA_LAYERS];
+  int bias_off[N_MMA_LAYERS];
+  int sig_w, sig_b, col_w, col_b;
+};
+
+__global__ void pack_weights_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed, PackParams pp) {
+  // one thread per 16-byte chunk (8 bf16) of the packed image
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= PACKED_W_BYTES / 16) {
+    const int a = gid - PACKED_W_BYTES / 16;  // one aux float per thread
+    if (a >= AUX_FLOATS) return;
+    float v = 0.f;
+    if (a < AUX_SIG_W) {
+      const int L = a / 256, i = a % 256;
+      v = i < layer_n(L) ? params[pp.bias_off[L] + i] : 0.f;
+    } else if (a < AUX_COL_W)
+      v = params[pp.sig_w + (a - AUX_SIG_W)];
+    else if (a < AUX_SIG_B)
+      v = params[pp.col_w + (a - AUX_COL_W)];
+    else if (a == AUX_SIG_B)
+      v = params[pp.sig_b];
+    else if (a < AUX_COL_B + 3)
+      v = params[pp.col_b + (a - AUX_COL_B)];
+    reinterpret_cast<float*>(packed + PACKED_W_BYTES)[a] = v;
+    return;
+  }
+  int byte = gid * 16, L = 0, kc = 0;
+  for (L = 0; L < N_MMA_LAYERS; ++L) {
+    const int lb = layer_chunks(L) * chunk_bytes(L);
+    if (byte < lb) break;
+    byte -= lb;
+  }
+  kc = byte / chunk_bytes(L);
+  byte -= kc * chunk_bytes(L);
+  const int n = byte / 128;
+  const int jphys = (byte % 128) / 16;
+  const int j = jphys ^ (n & 7);  // logical 16-byte chunk stored at this swizzled position
+  const PackLayer pl = pp.layer[L];
+  uint32_t out[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = j * 8 + e * 2 + h;  // K index inside the chunk
+      int col = -1;                      // source column in the (out,in) matrix
+      if (L == 0)
+        col = k < 60 ? k : -1;
+      else if (L == 4)
+        col = kc < 4 ? kc * 64 + k : (k < 60 ? 256 + k : -1);  // [hidden | xyz enc] (nerf.py:109)
+      else if (L == 9)
+        col = kc < 4 ? 24 + kc * 64 + k : (k < 24 ? k : -1);   // [dir enc | point_info] (nerf.py:118), info first in K
+      else
+        col = kc * 64 + k;
+      v[h] = col >= 0 ? params[pl.w_off + (int64_t)n * pl.ld + col] : 0.f;
+    }
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[0], v[1]);
+    out[e] = *reinterpret_cast<uint32_t*>(&b);
+  }
+  *reinterpret_cast<uint4*>(packed + (size_t)gid * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+const int kMmaLayerIndex[N_MMA_LAYERS] = {L_P0, L_P1, L_P2, L_P3, L_P4, L_P5, L_P6, L_P7, L_INFO, L_DIR};
+
+}  // namespace
+
+size_t nt_mlp_tc_packed_bytes() { return PACKED_BYTES; }
+
+int nt_mlp_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t st) {
+  const LayerTable T = nt_layers();
+  PackParams pp;
+  for (int i = 0; i < N_MMA_LAYERS; ++i) {
+    const int li = kMmaLayerIndex[i];
+    pp.layer[i].w_off = (int)T.w[li];
+    pp.layer[i].ld = kLayerIn[li];
+    pp.layer[i].n = kLayerOut[li];
+    pp.bias_off[i] = (int)T.b[li];
+  }
+  pp.sig_w = (int)T.w[L_SIGMA];
+  pp.sig_b = (int)T.b[L_SIGMA];
+  pp.col_w = (int)T.w[L_COLOR];
+  pp.col_b = (int)T.b[L_COLOR];
+  const int threads = PACKED_W_BYTES / 16 + AUX_FLOATS;
+  pack_weights_kernel<<<(threads + 255) / 256, 256, 0, st>>>(params, (uint8_t*)packed, pp);
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
+
+int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                          const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int dbg_layer,
+                          cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  TcParams P;
+  P.t = t;
+  P.rays = rays;
+  P.dir_enc = dir_enc;
+  P.params = params;
+  P.packed = (const uint8_t*)packed;
+  P.rgb = rgb;
+  P.sigma = sigma;
+  P.dbg = dbg;
+  P.dbg_layer = dbg_layer;
+  P.total = n * p;
+  P.p = p;
+  const int64_t tiles = (P.total + TILE_M - 1) / TILE_M;
+  P.num_pairs = (int)((tiles + 1) / 2);
+  if (P.num_pairs == 0) return NT_OK;
+  int grid = ctx->sm_count < P.num_pairs ? ctx->sm_count : P.num_pairs;
+  mlp_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
+
+int nt_mlp_tc_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                      const float* params, const void* packed, float* rgb, float* sigma, cudaStream_t st) {
+  return nt_mlp_tc_forward_dbg(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, nullptr, -1, st);
+}

@@ -77,6 +77,14 @@ class Context:
                                            _p(rgb), _p(sigma), _p(ws), ws.numel(), 1 if train else 0, _st()))
         return rgb, sigma, ws
 
+    def mlp_forward_debug(self, t, rays, dir_enc, flat, packed, layer):
+        n, p = t.shape
+        rgb, sigma = self._f(n, p, 3), self._f(n, p)
+        dbg = torch.zeros(n * p, 256, dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.nt_mlp_forward_debug(self.h, n, p, _p(t), _p(rays), _p(dir_enc), _p(flat), _p(packed), _p(rgb),
+                                                 _p(sigma), _p(dbg), layer, _st()))
+        return rgb, sigma, dbg
+
     def mlp_backward(self, precision, t, rays, dir_enc, flat, packed, g_rgb, g_sigma, ws, need_gt=True):
         n, p = t.shape
         grads = torch.zeros_like(flat)

@@ -334,3 +334,68 @@ def test_autograd_and_train_step_agree(dev, golden_dir):
     rel = float((g_auto - g_fused).norm() / g_fused.norm())
     assert rel < 1e-5, rel
     assert float(g_fused.norm()) > 0
+
+
+# ------------------------------------------------------------------------------------------------ bf16 tcgen05 path
+def _bf16_layers_ref(sd, g, tk):
+    """fp32 oracle activations of every tensor-core layer for the goldens' samples."""
+    d_cam, d_wrd = g["d_cam"], g["d_wrd"]
+    t = torch.from_numpy(g[tk])
+    pts = torch.from_numpy(O.sample_points(d_cam, g[tk], g["c2w"]))
+    dirs = torch.from_numpy(d_wrd)[:, None, :].expand(t.shape[0], t.shape[1], 3)
+    with torch.no_grad():
+        color, sigma, acts = O.network_forward(sd, O.encode(pts, 10), O.encode(dirs, 4), return_acts=True)
+    return color, sigma.squeeze(-1), acts
+
+
+@pytest.mark.parametrize("case", ["kat8", "fern64", "fern64_trained"])
+def test_mlp_bf16_layers(ctx, dev, golden_dir, case):
+    """Layer-by-layer: tcgen05 output of each of the 10 MMA layers vs the fp32 oracle (bf16 operand rounding only)."""
+    g = load(golden_dir, case)
+    sd = sd_of(case)
+    flat = flat_of(sd, dev)
+    packed = ctx.pack(flat, BF16)
+    rays, _, de = ctx.raygen(cu(g["row"], dev), cu(g["col"], dev), cu(g["c2w"], dev), cu(g["k_inv"], dev))
+    for tk in ("t_coarse", "t_fine"):
+        color, sigma, acts = _bf16_layers_ref(sd, g, tk)
+        report = {}
+        for L in range(10):
+            rgb, sig, dbg = ctx.mlp_forward_debug(cu(g[tk], dev), rays, de, flat, packed, L)
+            ref = acts[L].reshape(-1, acts[L].shape[-1]).numpy()
+            got = dbg.cpu().numpy()[:, :ref.shape[1]]
+            report[L] = float(np.abs(got - ref).max() / max(1e-6, np.abs(ref).max()))
+        print(case, tk, {k: "%.1e" % v for k, v in report.items()})
+        bad = {k: v for k, v in report.items() if not v < 3e-2}
+        assert not bad, bad
+        assert np.abs(rgb.cpu().numpy() - color.numpy()).max() <= 1e-2            # north_star bf16 tolerance
+        s_ref = sigma.numpy()
+        assert np.abs(sig.cpu().numpy() - s_ref).max() <= 3e-2 * max(1.0, np.abs(s_ref).max())
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_forward_bf16_matches_reference(dev, golden_dir, case):
+    g = load(golden_dir, case)
+    m = model_of(case, dev, "bf16")
+    with torch.no_grad():
+        cc, cf = m(torch.from_numpy(g["row"]), torch.from_numpy(g["col"]), torch.from_numpy(g["poses_bound"]),
+                   torch.from_numpy(g["k_inv"]))
+    ec = np.abs(cc.cpu().numpy() - g["c_coarse"]).max()
+    ef = np.abs(cf.cpu().numpy() - g["c_fine"]).max()
+    print(case, "bf16 max-abs err  C_coarse %.2e  C_fine %.2e" % (ec, ef))
+    assert ec <= 1e-2 and ef <= 1e-2          # north_star bf16 tolerance
+
+
+def test_bf16_ragged_sizes(ctx, dev, golden_dir):
+    """Tile tails: sample counts that are not multiples of the 256-sample tile pair, vs the fp32 CUDA path."""
+    g = load(golden_dir, "fern64")
+    sd = sd_of("fern64")
+    flat = flat_of(sd, dev)
+    packed = ctx.pack(flat, BF16)
+    rays, _, de = ctx.raygen(cu(g["row"], dev), cu(g["col"], dev), cu(g["c2w"], dev), cu(g["k_inv"], dev))
+    for n in (1, 3, 5, 64):
+        for tk in ("t_coarse", "t_fine"):
+            t = cu(g[tk][:n], dev)
+            r32, s32, _ = ctx.mlp_forward(FP32, t, rays[:n].contiguous(), de[:n].contiguous(), flat)
+            r16, s16, _ = ctx.mlp_forward(BF16, t, rays[:n].contiguous(), de[:n].contiguous(), flat, packed)
+            assert float((r32 - r16).abs().max()) <= 1e-2
+            assert float((s32 - s16).abs().max()) <= 3e-2 * max(1.0, float(s32.abs().max()))
