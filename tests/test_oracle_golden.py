@@ -9,7 +9,7 @@ import torch
 
 from oracle import nerf_oracle as O
 
-CASES = ["kat8", "lego48", "lego48_trained", "fern64", "fern64_trained"]
+CASES = ["kat8", "lego48", "lego48_trained", "fern64", "fern64_trained", "trained64"]
 
 
 def _bits(a):
@@ -17,6 +17,9 @@ def _bits(a):
 
 
 def _sd(case):
+    if case == "trained64":      # weights the reference itself trained (oracle/make_trained_golden.py), stored as fp16
+        z = np.load(os.path.join(os.path.dirname(__file__), "golden", "trained_weights_fp16.npz"))
+        return {k: torch.from_numpy(z[k].astype(np.float32)) for k in z.files if not k.startswith("__")}
     sd = O.init_state_dict(624)
     return O.trained_like(sd) if case.endswith("trained") else sd
 
