@@ -123,3 +123,7 @@ int nt_mlp_tc_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float
 int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                           const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int dbg_layer,
                           cudaStream_t st);
+// composite_fine_fwd.cu
+int nt_launch_composite_fine_fwd(nt_ctx* ctx, int64_t n, const float* t_c, const float* rgb_c, const float* sigma_c,
+                                 const float* t_f, const float* rgb_f, const float* sigma_f, float last, float* c_out,
+                                 float* weights, uint8_t* perm, cudaStream_t st);

@@ -365,12 +365,11 @@ extern "C" int nt_composite_fine(nt_ctx* ctx, int64_t n, const float* t_c, const
   NT_REQUIRE(ctx && t_c && rgb_c && sigma_c && t_f && rgb_f && sigma_f && c_out, "null pointer");
   NT_REQUIRE(ctx->n_coarse + ctx->n_fine == 192, "fine compositing is built for Nc+Nf=192");
   if (n <= 0) return NT_OK;
-  composite_fine_kernel<false><<<(unsigned)((n + FINE_WARPS - 1) / FINE_WARPS), FINE_WARPS * 32, 0,
-                                 (cudaStream_t)stream>>>(n, ctx->n_coarse, ctx->n_fine, t_c, rgb_c, sigma_c, t_f, rgb_f,
-                                                         sigma_f, last, c_out, weights, perm, nullptr, nullptr, nullptr,
-                                                         nullptr, nullptr, nullptr, nullptr);
-  NT_LAUNCH_CHECK(ctx);
-  return NT_OK;
+  NT_REQUIRE(ctx->n_coarse == 64 && ctx->n_fine == 128, "fine compositing is built for Nc=64, Nf=128");
+  // forward: the five channel sorts run in registers (composite_fine_fwd.cu); the shared-memory kernel above is
+  // kept for the backward pass, which re-gathers through the stored permutations
+  return nt_launch_composite_fine_fwd(ctx, n, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, last, c_out, weights, perm,
+                                      (cudaStream_t)stream);
 }
 
 extern "C" int nt_composite_fine_backward(nt_ctx* ctx, int64_t n, const float* t_c, const float* rgb_c,

@@ -9,9 +9,9 @@
 //     BOTH tiles before it is released (weights cross L2->SMEM once per 256 samples);
 //   * one elected thread issues tcgen05.mma (M=128, N=256|128, K=16, bf16 -> fp32) accumulating in TMEM
 //     (tile A: columns 0-255, tile B: 256-511);
-//   * the epilogue warps read the accumulator with tcgen05.ld, add bias, apply ReLU, round to bf16 and write the
-//     next layer's A operand in place; the sigma head (256->1, abs) and colour head (128->3, sigmoid) are evaluated
-//     on CUDA cores from the fp32 accumulators in the same pass.
+//   * the epilogue warps read the accumulator with tcgen05.ld (double-buffered), add bias, apply ReLU, round to
+//     bf16 and write the next layer's A operand in place; the sigma head (256->1, abs) and colour head (128->3,
+//     sigmoid) are evaluated on CUDA cores from the fp32 accumulators in the same pass.
 // Skip (nerf.py:109) and view (nerf.py:118) concatenations are extra K-chunks accumulated into the same TMEM tile.
 #include <cuda_bf16.h>
 
@@ -28,9 +28,12 @@ constexpr int OFF_ACT = 0;
 constexpr int OFF_ENC = 2 * ACT_BYTES;
 constexpr int OFF_W = OFF_ENC + 2 * CHUNK_A_BYTES;
 constexpr int OFF_BAR = OFF_W + N_STAGES * W_STAGE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int OFF_SCRATCH = OFF_BAR + 128;         // sigma-head partial sums: 2 tiles x 128 rows fp32
+constexpr int SMEM_BYTES = OFF_SCRATCH + 2 * TILE_M * 4;
 constexpr int N_MMA_LAYERS = 10;  // L0..L7, point_info, dir_info
-constexpr int N_THREADS = 320;    // 8 epilogue warps + TMA producer + MMA issuer
+constexpr int N_EPI_WARPS = 16;   // per tile: 4 lane quadrants x 2 column halves
+constexpr int WARP_TMA = 16, WARP_MMA = 17;
+constexpr int N_THREADS = 576;    // 16 epilogue warps + TMA producer + MMA issuer
 
 // barrier slots (8 B each) inside the OFF_BAR block
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = 2, BAR_ACC_FULL = 4, BAR_ACT_READY = 6, BAR_COUNT = 8 };
@@ -46,11 +49,11 @@ constexpr int total_packed_bytes() {
 constexpr int PACKED_W_BYTES = total_packed_bytes();  // 1 196 032
 // fp32 side block appended to the packed weights, 16-byte aligned (the flat parameter buffer is not: the
 // 1-wide sigma bias shifts everything after it by one float)
-constexpr int AUX_BIAS = 0;            // 10 x 256
-constexpr int AUX_SIG_W = 2560;        // 256
-constexpr int AUX_COL_W = 2816;        // 3 x 128
+constexpr int AUX_BIAS = 0;      // 10 x 256
+constexpr int AUX_SIG_W = 2560;  // 256
+constexpr int AUX_COL_W = 2816;  // 3 x 128
 constexpr int AUX_SIG_B = 3200;
-constexpr int AUX_COL_B = 3201;        // 3
+constexpr int AUX_COL_B = 3201;  // 3
 constexpr int AUX_FLOATS = 3208;
 constexpr int PACKED_BYTES = PACKED_W_BYTES + AUX_FLOATS * 4;
 
@@ -142,8 +145,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+// asynchronous TMEM -> register load of 32 consecutive fp32 columns of this thread's lane; the registers may only
+// be read after tmem_ld_wait() on the same array (the "+r" operands make that a data dependency for the compiler)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -154,25 +158,156 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo -> lower address
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // lo -> lower address
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// A-operand row `row`, 16-byte chunk `j` (0..7) of a [128 x 64] bf16 SW128 tile at `tile`
-__device__ __forceinline__ uint32_t a_chunk_addr(uint32_t tile, int row, int j) {
-  return tile + row * 128 + ((j ^ (row & 7)) << 4);
+// sin/cos for the bf16 path: 2-term Cody-Waite reduction by 2*pi, then the SFU (abs err ~1e-6, far below bf16's 4e-3)
+__device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, x);
+  r = fmaf(k, 1.7484555314695172e-07f, r);
+  s = __sinf(r);
+  c = __cosf(r);
+}
+
+// per-thread view of the shared-memory operand tiles: row `row` of a [128 x 64] bf16 SW128 tile lives at
+// tile + row*128, its 16-byte chunk j at ((j ^ (row & 7)) << 4)
+struct RowSwz {
+  uint32_t row_off;  // row * 128
+  uint32_t x4;       // (row & 7) << 4
+  __device__ __forceinline__ uint32_t addr(uint32_t tile, int j) const { return tile + row_off + (x4 ^ (uint32_t)(j << 4)); }
+};
+
+enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_COLOUR = 3 };
+
+// One layer's epilogue for one thread: the thread owns one sample (= one TMEM lane) and one half of the layer's
+// output columns.  accumulator -> +bias -> activation -> bf16 A operand of the next layer (or the heads).
+// 16 epilogue warps (4 per scheduler) hide the TMEM / bias-load latencies by thread-level parallelism.
+template <int KIND, bool DBG>
+__device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int half, uint32_t tmem_row, uint32_t act,
+                                               uint32_t scratch, uint32_t enc, int pair_bar, const RowSwz sw, int row,
+                                               const float* __restrict__ aux, int64_t s, bool valid) {
+  constexpr int NCB = KIND == EPI_COLOUR ? 2 : 4;  // 32-column blocks per half
+  const int cb0 = half * NCB;
+  float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCB; ++i) {
+    const int cb = cb0 + i;
+    uint32_t raw[32];
+    tmem_ld32_issue(tmem_row + cb * 32, raw);
+    const float4* __restrict__ bias4 = reinterpret_cast<const float4*>(aux + AUX_BIAS + L * 256 + cb * 32);
+    float4 b4[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b4[j] = __ldg(bias4 + j);
+    tmem_ld_wait(raw);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b4[j].x;
+      v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4[j].y;
+      v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4[j].z;
+      v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4[j].w;
+    }
+    if (DBG) {
+      if (P.dbg_layer == L && valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) P.dbg[s * 256 + cb * 32 + j] = (KIND == EPI_LINEAR) ? v[j] : fmaxf(v[j], 0.f);
+      }
+    }
+    if (KIND == EPI_RELU_SIGMA) {  // sigma head from the fp32 activations (nerf.py:94, :114)
+      const float4* __restrict__ ws = reinterpret_cast<const float4*>(aux + AUX_SIG_W + cb * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w4 = __ldg(ws + j);
+        sig_acc = fmaf(fmaxf(v[4 * j + 0], 0.f), w4.x, sig_acc);
+        sig_acc = fmaf(fmaxf(v[4 * j + 1], 0.f), w4.y, sig_acc);
+        sig_acc = fmaf(fmaxf(v[4 * j + 2], 0.f), w4.z, sig_acc);
+        sig_acc = fmaf(fmaxf(v[4 * j + 3], 0.f), w4.w, sig_acc);
+      }
+    }
+    if (KIND == EPI_COLOUR) {  // colour head (nerf.py:99, :119) on u = relu(.)
+      const float4* __restrict__ wc = reinterpret_cast<const float4*>(aux + AUX_COL_W + cb * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w0 = __ldg(wc + j), w1 = __ldg(wc + 32 + j), w2 = __ldg(wc + 64 + j);
+        const float u0 = fmaxf(v[4 * j], 0.f), u1 = fmaxf(v[4 * j + 1], 0.f), u2 = fmaxf(v[4 * j + 2], 0.f),
+                    u3 = fmaxf(v[4 * j + 3], 0.f);
+        c0 = fmaf(u0, w0.x, fmaf(u1, w0.y, fmaf(u2, w0.z, fmaf(u3, w0.w, c0))));
+        c1 = fmaf(u0, w1.x, fmaf(u1, w1.y, fmaf(u2, w1.z, fmaf(u3, w1.w, c1))));
+        c2 = fmaf(u0, w2.x, fmaf(u1, w2.y, fmaf(u2, w2.z, fmaf(u3, w2.w, c2))));
+      }
+    } else {  // next layer's A operand: K-chunk cb/2, 16-byte chunks (cb%2)*4 .. +3
+      const uint32_t dst = act + (cb >> 1) * CHUNK_A_BYTES;
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          w[e] = KIND == EPI_LINEAR ? pack_bf16(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1])
+                                    : pack_bf16_relu(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1]);
+        st_shared_v4(sw.addr(dst, (cb & 1) * 4 + qd), w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  // ---- heads: the two column halves of a row live in warps w and w+8; combine through shared memory ----
+  if (KIND == EPI_RELU_SIGMA) {
+    if (half == 1) asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + row * 4), "f"(sig_acc) : "memory");
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    if (half == 0) {
+      float other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(scratch + row * 4) : "memory");
+      if (valid) P.sigma[s] = fabsf(sig_acc + other + __ldg(aux + AUX_SIG_B));
+    }
+  }
+  if (KIND == EPI_COLOUR) {
+    // the view-feature tile is free (every MMA of this pair has retired): use its first 2 KB as scratch
+    if (half == 1)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(enc + row * 16), "f"(c0), "f"(c1), "f"(c2), "f"(0.f)
+                   : "memory");
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    if (half == 0) {
+      float o0, o1, o2, o3;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(o0), "=f"(o1), "=f"(o2), "=f"(o3)
+                   : "r"(enc + row * 16)
+                   : "memory");
+      if (valid) {
+        P.rgb[s * 3 + 0] = 1.f / (1.f + __expf(-(c0 + o0 + __ldg(aux + AUX_COL_B))));
+        P.rgb[s * 3 + 1] = 1.f / (1.f + __expf(-(c1 + o1 + __ldg(aux + AUX_COL_B + 1))));
+        P.rgb[s * 3 + 2] = 1.f / (1.f + __expf(-(c2 + o2 + __ldg(aux + AUX_COL_B + 2))));
+      }
+    }
+    // the next pair's encoder overwrites this scratch: make sure the reader is done first
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
+template <bool DBG>
 __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -189,17 +324,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
     }
     for (int tl = 0; tl < 2; ++tl) {
       mbar_init(bar(BAR_ACC_FULL + tl), 1);
-      mbar_init(bar(BAR_ACT_READY + tl), TILE_M);
+      mbar_init(bar(BAR_ACT_READY + tl), 2 * TILE_M);
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc_512(smem_u32(tmem_slot));
+  if (warp == WARP_MMA) tmem_alloc_512(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == WARP_TMA) {
     // ===================== TMA producer: weight K-chunks, same order for every tile pair =====================
     if (lane == 0) {
       uint32_t q = 0;
@@ -217,7 +352,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == WARP_MMA) {
     // ===================== MMA issuer: one thread drives the tensor core for both tiles =====================
     if (lane == 0) {
       uint32_t q = 0, lit = 0;
@@ -251,13 +386,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
       }
     }
   } else {
-    // ===================== encode + epilogue warps: 4 per tile, one sample (TMEM lane) per thread ===========
-    const int tl = warp >> 2;
+    // ===================== encode + epilogue warps: per tile 4 lane quadrants x 2 column halves =============
+    const int tl = (warp >> 2) & 1;
+    const int half = warp >> 3;
     const int row = (warp & 3) * 32 + lane;
+    const int pair_bar = 1 + (warp & 7);  // named barrier shared by the two warps that own the same rows
     const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
     const uint32_t enc = sbase + OFF_ENC + tl * CHUNK_A_BYTES;
+    const uint32_t scratch = sbase + OFF_SCRATCH + tl * TILE_M * 4;
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + tl * 256;
     const float* __restrict__ aux = reinterpret_cast<const float*>(P.packed + PACKED_W_BYTES);
+    RowSwz sw;
+    sw.row_off = row * 128;
+    sw.x4 = (row & 7) << 4;
     uint32_t it = 0;
     for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
       const int64_t s = ((int64_t)pair * 2 + tl) * TILE_M + row;
@@ -265,6 +406,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
       const int64_t sc = valid ? s : P.total - 1;
       const int64_t ray = sc / P.p;
       // ---- positional encoding of this sample (nerf.py:200-216, 135-167) -> enc tile, bf16, swizzled ----
+      // half 0 produces feature pairs 0..15 (16-byte chunks 0-3), half 1 pairs 16..29 + zero padding (chunks 4-7)
       {
         const float4* rp = reinterpret_cast<const float4*>(P.rays + ray * 16);
         const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
@@ -274,19 +416,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
         pos[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.w, pc0), __fmul_rn(r1.x, pc1)), __fmul_rn(r1.y, pc2)), r3.x);
         pos[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.z, pc0), __fmul_rn(r1.w, pc1)), __fmul_rn(r2.x, pc2)), r3.y);
         pos[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.y, pc0), __fmul_rn(r2.z, pc1)), __fmul_rn(r2.w, pc2)), r3.z);
-        uint32_t f[32];
+        uint32_t f[16];
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int l = 0; l < 10; ++l) {
+        for (int i = 0; i < 16; ++i) {
+          const int pi = half * 16 + i;  // feature pair index = c*10 + l
+          if (pi < 30) {
+            const int c = pi / 10, l = pi % 10;
+            const float x = c == 0 ? pos[0] : (c == 1 ? pos[1] : pos[2]);
             float sn, cs;
-            sincosf(__fmul_rn(__uint_as_float(c_tc_freq_point[l]), pos[c]), &sn, &cs);
-            f[c * 10 + l] = pack_bf16(sn, cs);  // features (c*20+2l, c*20+2l+1)
+            fast_sincos(__fmul_rn(__uint_as_float(c_tc_freq_point[l]), x), sn, cs);
+            f[i] = pack_bf16(sn, cs);  // features (c*20+2l, c*20+2l+1)
+          } else {
+            f[i] = 0u;  // K padded 60 -> 64
           }
-        f[30] = 0u;
-        f[31] = 0u;  // K padded 60 -> 64
+        }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) st_shared_v4(a_chunk_addr(enc, row, j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(sw.addr(enc, half * 4 + j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -295,79 +441,35 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
       for (int L = 0; L < N_MMA_LAYERS; ++L, ++it) {
         mbar_wait(bar(BAR_ACC_FULL + tl), it & 1);
         tc_fence_after();
-        const float* __restrict__ bias = aux + AUX_BIAS + L * 256;
-        const int ncb = layer_n(L) / 32;
-        float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-        for (int cb = 0; cb < ncb; ++cb) {
-          float v[32];
-          tmem_ld32(tmem_row + cb * 32, v);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cb * 32 + j));
-            v[j] += b4.x;
-            v[j + 1] += b4.y;
-            v[j + 2] += b4.z;
-            v[j + 3] += b4.w;
-          }
-          if (L != 8) {  // point_info has no activation (nerf.py:117)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (P.dbg && P.dbg_layer == L && valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) P.dbg[s * 256 + cb * 32 + j] = v[j];
-          }
-          if (L == 7) {  // sigma head from the fp32 activations (nerf.py:94, :114)
-            const float* __restrict__ ws = aux + AUX_SIG_W + cb * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(ws + j));
-              sig_acc = fmaf(v[j], w4.x, sig_acc);
-              sig_acc = fmaf(v[j + 1], w4.y, sig_acc);
-              sig_acc = fmaf(v[j + 2], w4.z, sig_acc);
-              sig_acc = fmaf(v[j + 3], w4.w, sig_acc);
-            }
-          }
-          if (L == 9) {  // colour head (nerf.py:99, :119)
-            const float* __restrict__ wc = aux + AUX_COL_W + cb * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              c0 = fmaf(v[j], __ldg(wc + j), c0);
-              c1 = fmaf(v[j], __ldg(wc + 128 + j), c1);
-              c2 = fmaf(v[j], __ldg(wc + 256 + j), c2);
-            }
-          } else {  // next layer's A operand: K-chunk cb/2, 16-byte chunks (cb%2)*4 .. +3
-            const uint32_t dst = act + (cb >> 1) * CHUNK_A_BYTES;
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-              st_shared_v4(a_chunk_addr(dst, row, (cb & 1) * 4 + qd), pack_bf16(v[8 * qd], v[8 * qd + 1]),
-                           pack_bf16(v[8 * qd + 2], v[8 * qd + 3]), pack_bf16(v[8 * qd + 4], v[8 * qd + 5]),
-                           pack_bf16(v[8 * qd + 6], v[8 * qd + 7]));
-          }
-        }
+        if (L == 7)
+          epilogue_layer<EPI_RELU_SIGMA, DBG>(P, L, half, tmem_row, act, scratch, enc, pair_bar, sw, row, aux, s, valid);
+        else if (L == 8)
+          epilogue_layer<EPI_LINEAR, DBG>(P, L, half, tmem_row, act, scratch, enc, pair_bar, sw, row, aux, s, valid);
+        else if (L == 9)
+          epilogue_layer<EPI_COLOUR, DBG>(P, L, half, tmem_row, act, scratch, enc, pair_bar, sw, row, aux, s, valid);
+        else
+          epilogue_layer<EPI_RELU, DBG>(P, L, half, tmem_row, act, scratch, enc, pair_bar, sw, row, aux, s, valid);
         if (L == 4) {
           // all MMAs that read the xyz features have retired: reuse the tile for the view-direction features
-          const float4* de = reinterpret_cast<const float4*>(P.dir_enc + ray * 24);
-          uint32_t f[12];
+          // (24 features = 16-byte chunks 0-2 by half 0; zero chunks 3-7 split between the halves)
+          if (half == 0) {
+            const float4* de = reinterpret_cast<const float4*>(P.dir_enc + ray * 24);
+            uint32_t f[12];
 #pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const float4 d4 = __ldg(de + j);
-            f[2 * j] = pack_bf16(d4.x, d4.y);
-            f[2 * j + 1] = pack_bf16(d4.z, d4.w);
+            for (int j = 0; j < 6; ++j) {
+              const float4 d4 = __ldg(de + j);
+              f[2 * j] = pack_bf16(d4.x, d4.y);
+              f[2 * j + 1] = pack_bf16(d4.z, d4.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) st_shared_v4(sw.addr(enc, j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            st_shared_v4(sw.addr(enc, 3), 0u, 0u, 0u, 0u);
+          } else {
+#pragma unroll
+            for (int j = 4; j < 8; ++j) st_shared_v4(sw.addr(enc, j), 0u, 0u, 0u, 0u);
           }
-#pragma unroll
-          for (int j = 0; j < 3; ++j) st_shared_v4(a_chunk_addr(enc, row, j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-#pragma unroll
-          for (int j = 3; j < 8; ++j) st_shared_v4(a_chunk_addr(enc, row, j), 0u, 0u, 0u, 0u);
         }
-        if (L == 7 && valid) P.sigma[s] = fabsf(sig_acc + __ldg(aux + AUX_SIG_B));
-        if (L == 9) {
-          if (valid) {
-            P.rgb[s * 3 + 0] = 1.f / (1.f + __expf(-(c0 + __ldg(aux + AUX_COL_B))));
-            P.rgb[s * 3 + 1] = 1.f / (1.f + __expf(-(c1 + __ldg(aux + AUX_COL_B + 1))));
-            P.rgb[s * 3 + 2] = 1.f / (1.f + __expf(-(c2 + __ldg(aux + AUX_COL_B + 2))));
-          }
-        } else {
+        if (L != 9) {
           fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
           tc_fence_before();
           mbar_arrive(bar(BAR_ACT_READY + tl));
@@ -379,7 +481,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     tmem_dealloc_512(tmem_base);
   }
@@ -398,10 +500,10 @@ struct PackParams {
 };
 
 __global__ void pack_weights_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed, PackParams pp) {
-  // one thread per 16-byte chunk (8 bf16) of the packed image
+  // one thread per 16-byte chunk (8 bf16) of the packed image, then one per float of the fp32 side block
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= PACKED_W_BYTES / 16) {
-    const int a = gid - PACKED_W_BYTES / 16;  // one aux float per thread
+    const int a = gid - PACKED_W_BYTES / 16;
     if (a >= AUX_FLOATS) return;
     float v = 0.f;
     if (a < AUX_SIG_W) {
@@ -485,7 +587,8 @@ int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const f
                           cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   TcParams P;
@@ -504,7 +607,10 @@ int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const f
   P.num_pairs = (int)((tiles + 1) / 2);
   if (P.num_pairs == 0) return NT_OK;
   int grid = ctx->sm_count < P.num_pairs ? ctx->sm_count : P.num_pairs;
-  mlp_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
+  if (dbg)
+    mlp_tc_kernel<true><<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
+  else
+    mlp_tc_kernel<false><<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;
 }

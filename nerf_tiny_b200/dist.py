@@ -1,0 +1,81 @@
+"""Ray sharding across the GPUs of one box: one process per GPU, torch.distributed for plumbing.
+
+Rays are independent, so each rank renders a contiguous slice with replicated weights and no data-path
+collective.  Two quantities of the reference are *batch-global* and must be agreed on so that
+sharded == unsharded bit for bit:
+  * any_step_zero — numpy's linspace switches formula for EVERY ray if any ray has step == 0 (nerf.py:288)
+  * delta0        — resample uses t_coarse[0,1] - t_coarse[0,0] of the batch's FIRST ray for all rays (nerf.py:234)
+Training adds one SUM all-reduce of the flat gradient (the loss is a sum over rays, nerf.py:328-331).
+Host logic only (numpy + torch.distributed); works with the gloo backend on CPU, which is how it is tested.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+f32 = np.float32
+
+
+def shard_slice(n: int, rank: int, world: int) -> slice:
+    """Contiguous ceil(n/world)-sized slices; the last ranks may get fewer (or zero) rays."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return slice(lo, min(n, lo + per))
+
+
+def step_is_zero(near: np.ndarray, far: np.ndarray, n_coarse: int = 64) -> bool:
+    near = np.asarray(near, dtype=f32)
+    far = np.asarray(far, dtype=f32)
+    step = ((far - near).astype(f32) / f32(n_coarse - 1)).astype(f32)
+    return bool(np.any(step == 0))
+
+
+def delta0_of(near0: float, far0: float, any_step_zero: bool, n_coarse: int = 64) -> np.float32:
+    """t_coarse[0,1] - t_coarse[0,0] exactly as np.linspace produces them in fp32."""
+    a, b = f32(near0), f32(far0)
+    div = f32(n_coarse - 1)
+    delta = f32(b - a)
+    if any_step_zero:
+        t0 = f32(f32(f32(f32(0) / div) * delta) + a)
+        t1 = f32(f32(f32(f32(1) / div) * delta) + a)
+    else:
+        step = f32(delta / div)
+        t0 = f32(f32(f32(0) * step) + a)
+        t1 = f32(f32(f32(1) * step) + a)
+    return f32(t1 - t0)
+
+
+def global_quantities(near_local: np.ndarray, far_local: np.ndarray, group=None, n_coarse: int = 64):
+    """(any_step_zero, delta0) of the GLOBAL batch, from each rank's local near/far (rank 0 owns global ray 0)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    flag = torch.tensor([1 if step_is_zero(near_local, far_local, n_coarse) else 0], dtype=torch.int32)
+    first = torch.zeros(2, dtype=torch.float32)
+    if rank == 0 and len(near_local) > 0:
+        first[0], first[1] = float(near_local[0]), float(far_local[0])
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        dist.broadcast(first, src=0, group=group)
+    zero = bool(flag.item())
+    return zero, delta0_of(first[0].item(), first[1].item(), zero, n_coarse)
+
+
+def allreduce_sum_(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
+    """One collective over the flat 593 924-float gradient (2 375 696 B); NCCL over NVLink on GPUs."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return flat_grad
+
+
+def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All ranks' [n_local, C] outputs -> [n_total, C] in ray order (render output gather, 12 B/ray)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    per = (n_total + world - 1) // world
+    pad = torch.zeros(per, *local.shape[1:], dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat(out, dim=0)[:n_total]

@@ -300,7 +300,7 @@ def net_out(sd, t: torch.Tensor, d_cam: np.ndarray, d_wrd: np.ndarray, c2w: np.n
 
 
 def render_rays(sd, row, col, c2w, k_inv, near, far, n_coarse: int = 64, n_fine: int = 128,
-                last: float = 1e-4, return_aux: bool = False):
+                last: float = 1e-4, return_aux: bool = False, any_step_zero=None, delta0=None):
     """nerf.py:286-323.  row/col int arrays [N]; c2w [N,4,4]; near/far [N] (fp32 numpy)."""
     near = np.asarray(near, dtype=f32)
     far = np.asarray(far, dtype=f32)
@@ -308,11 +308,12 @@ def render_rays(sd, row, col, c2w, k_inv, near, far, n_coarse: int = 64, n_fine:
     dt = next(iter(sd.values())).dtype
     npdt = np.float64 if dt == torch.float64 else f32
     d_cam, d_wrd = ray_dirs(row, col, np.asarray(k_inv, dtype=f32), c2w, f32=npdt)
-    t_c = torch.from_numpy(t_coarse_of(near, far, n_coarse)).to(dt)
+    # any_step_zero / delta0: batch-global quantities a ray shard is told explicitly
+    t_c = torch.from_numpy(linspace_rows(near, far, n_coarse, any_step_zero=any_step_zero)).to(dt)
     color_c, sigma_c = net_out(sd, t_c, d_cam, d_wrd, c2w)
     delta_c = torch.from_numpy(((far - near) / f32(n_coarse)).astype(f32)).to(dt)[:, None].expand(-1, n_coarse)
     w_c = get_density(delta_c, sigma_c)                                   # nerf.py:293-295
-    t_f, idx, u, cdf = resample(t_c, w_c, n_fine, return_aux=True)        # nerf.py:298
+    t_f, idx, u, cdf = resample(t_c, w_c, n_fine, delta0=delta0, return_aux=True)        # nerf.py:298
     color_f, sigma_f = net_out(sd, t_f, d_cam, d_wrd, c2w, t_requires_path=True)
     c_fine, w_f, t_s, _, _ = merge_sort_composite(t_c, color_c, sigma_c, t_f, color_f, sigma_f, last)
     c_coarse = color_cum(w_c, color_c)
@@ -323,12 +324,14 @@ def render_rays(sd, row, col, c2w, k_inv, near, far, n_coarse: int = 64, n_fine:
     return c_coarse, c_fine
 
 
-def forward(sd, row, col, poses_bound, k_inv, n_coarse: int = 64, n_fine: int = 128, return_aux: bool = False):
+def forward(sd, row, col, poses_bound, k_inv, n_coarse: int = 64, n_fine: int = 128, return_aux: bool = False,
+            any_step_zero=None, delta0=None):
     """nerf.py:333-348.  poses_bound [N,17] (float64 from the loader), cast to fp32 first."""
     pb = torch.as_tensor(poses_bound).to(torch.float32)
     c2w, _, _, _, near, far = poses_extract(pb)
     return render_rays(sd, np.asarray(row), np.asarray(col), c2w.numpy(), torch.as_tensor(k_inv).numpy(),
-                       near.numpy(), far.numpy(), n_coarse, n_fine, return_aux=return_aux)
+                       near.numpy(), far.numpy(), n_coarse, n_fine, return_aux=return_aux,
+                       any_step_zero=any_step_zero, delta0=delta0)
 
 
 def ray_loss(c_coarse, c_fine, c_true):
