@@ -28,15 +28,16 @@ constexpr int OFF_ACT = 0;
 constexpr int OFF_ENC = 2 * ACT_BYTES;
 constexpr int OFF_W = OFF_ENC + 2 * CHUNK_A_BYTES;
 constexpr int OFF_BAR = OFF_W + N_STAGES * W_STAGE_BYTES;
-constexpr int OFF_SCRATCH = OFF_BAR + 128;         // sigma-head partial sums: 2 tiles x 128 rows fp32
-constexpr int SMEM_BYTES = OFF_SCRATCH + 2 * TILE_M * 4;
+constexpr int AUX_REC_FLOATS = 640;                // per-layer fp32 record: bias[256] | head weights[384]
+constexpr int OFF_AUX = OFF_BAR + 128;             // single-buffered stage for the current layer's record
+constexpr int SMEM_BYTES = OFF_AUX + AUX_REC_FLOATS * 4;
 constexpr int N_MMA_LAYERS = 10;  // L0..L7, point_info, dir_info
 constexpr int N_EPI_WARPS = 16;   // per tile: 4 lane quadrants x 2 column halves
 constexpr int WARP_TMA = 16, WARP_MMA = 17;
 constexpr int N_THREADS = 576;    // 16 epilogue warps + TMA producer + MMA issuer
 
 // barrier slots (8 B each) inside the OFF_BAR block
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = 2, BAR_ACC_FULL = 4, BAR_ACT_READY = 6, BAR_COUNT = 8 };
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 2, BAR_ACC_FULL = 4, BAR_ACT_READY = 6, BAR_AUX_FULL = 8, BAR_COUNT = 9 };
 
 __host__ __device__ constexpr int layer_chunks(int L) { return L == 0 ? 1 : ((L == 4 || L == 9) ? 5 : 4); }
 __host__ __device__ constexpr int layer_n(int L) { return L == 9 ? 128 : 256; }
@@ -49,13 +50,15 @@ constexpr int total_packed_bytes() {
 constexpr int PACKED_W_BYTES = total_packed_bytes();  // 1 196 032
 // fp32 side block appended to the packed weights, 16-byte aligned (the flat parameter buffer is not: the
 // 1-wide sigma bias shifts everything after it by one float)
-constexpr int AUX_BIAS = 0;      // 10 x 256
-constexpr int AUX_SIG_W = 2560;  // 256
-constexpr int AUX_COL_W = 2816;  // 3 x 128
-constexpr int AUX_SIG_B = 3200;
-constexpr int AUX_COL_B = 3201;  // 3
-constexpr int AUX_FLOATS = 3208;
+// one record per tensor-core layer, TMA-copied into shared memory right before the layer's epilogue:
+//   [0,256)  bias (dir_info: 128 biases, then the 3 colour biases at 128..130)
+//   [256,640) head weights: layer 7 -> sigma weights [256] + sigma bias at 512; layer 9 -> colour weights [3][128]
+constexpr int AUX_EXTRA = 256;
+constexpr int AUX_SIG_B = 512;
+constexpr int AUX_COL_B = 128;
+constexpr int AUX_FLOATS = N_MMA_LAYERS * AUX_REC_FLOATS;
 constexpr int PACKED_BYTES = PACKED_W_BYTES + AUX_FLOATS * 4;
+__host__ __device__ constexpr int aux_bytes(int L) { return (L == 7 || L == 9) ? AUX_REC_FLOATS * 4 : 1024; }
 
 struct TcParams {
   const float* t;
@@ -202,13 +205,48 @@ struct RowSwz {
 
 enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_COLOUR = 3 };
 
+// diagnostic timeline (debug instantiation only, dbg_layer >= 100): clock64 stamps of block 0's first 4 tile pairs,
+// prof[(pair_local*10 + L)*16 + slot] as int64 inside the dbg buffer
+#define TC_PROF(slot)                                                                                        \
+  do {                                                                                                       \
+    if (DBG && P.dbg_layer >= 100 && blockIdx.x == 0 && pair_local < 4)                                      \
+      reinterpret_cast<long long*>(P.dbg)[(pair_local * 10 + L) * 16 + (slot)] = clock64();                  \
+  } while (0)
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+// single-column TMEM exchange between the two threads that own the same row (warps w and w+8 share a lane quadrant)
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+               : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float& a, float& b, float& c, float& d) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3)::"memory");
+  a = __uint_as_float(r0);
+  b = __uint_as_float(r1);
+  c = __uint_as_float(r2);
+  d = __uint_as_float(r3);
+}
+
 // One layer's epilogue for one thread: the thread owns one sample (= one TMEM lane) and one half of the layer's
 // output columns.  accumulator -> +bias -> activation -> bf16 A operand of the next layer (or the heads).
-// 16 epilogue warps (4 per scheduler) hide the TMEM / bias-load latencies by thread-level parallelism.
+// 16 epilogue warps (4 per scheduler) hide the TMEM latency by thread-level parallelism; biases and head weights
+// come from the layer's record in shared memory (broadcast LDS, staged by TMA while the MMAs run).
 template <int KIND, bool DBG>
 __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int half, uint32_t tmem_row, uint32_t act,
-                                               uint32_t scratch, uint32_t enc, int pair_bar, const RowSwz sw, int row,
-                                               const float* __restrict__ aux, int64_t s, bool valid) {
+                                               uint32_t aux_s, int pair_bar, const RowSwz sw, int64_t s, bool valid) {
   constexpr int NCB = KIND == EPI_COLOUR ? 2 : 4;  // 32-column blocks per half
   const int cb0 = half * NCB;
   float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
@@ -217,10 +255,10 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
     const int cb = cb0 + i;
     uint32_t raw[32];
     tmem_ld32_issue(tmem_row + cb * 32, raw);
-    const float4* __restrict__ bias4 = reinterpret_cast<const float4*>(aux + AUX_BIAS + L * 256 + cb * 32);
+    const uint32_t bias_s = aux_s + cb * 128;
     float4 b4[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) b4[j] = __ldg(bias4 + j);
+    for (int j = 0; j < 8; ++j) b4[j] = lds128(bias_s + j * 16);
     tmem_ld_wait(raw);
     float v[32];
 #pragma unroll
@@ -237,10 +275,10 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
       }
     }
     if (KIND == EPI_RELU_SIGMA) {  // sigma head from the fp32 activations (nerf.py:94, :114)
-      const float4* __restrict__ ws = reinterpret_cast<const float4*>(aux + AUX_SIG_W + cb * 32);
+      const uint32_t ws = aux_s + (AUX_EXTRA + cb * 32) * 4;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 w4 = __ldg(ws + j);
+        const float4 w4 = lds128(ws + j * 16);
         sig_acc = fmaf(fmaxf(v[4 * j + 0], 0.f), w4.x, sig_acc);
         sig_acc = fmaf(fmaxf(v[4 * j + 1], 0.f), w4.y, sig_acc);
         sig_acc = fmaf(fmaxf(v[4 * j + 2], 0.f), w4.z, sig_acc);
@@ -248,10 +286,10 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
       }
     }
     if (KIND == EPI_COLOUR) {  // colour head (nerf.py:99, :119) on u = relu(.)
-      const float4* __restrict__ wc = reinterpret_cast<const float4*>(aux + AUX_COL_W + cb * 32);
+      const uint32_t wc = aux_s + (AUX_EXTRA + cb * 32) * 4;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 w0 = __ldg(wc + j), w1 = __ldg(wc + 32 + j), w2 = __ldg(wc + 64 + j);
+        const float4 w0 = lds128(wc + j * 16), w1 = lds128(wc + 512 + j * 16), w2 = lds128(wc + 1024 + j * 16);
         const float u0 = fmaxf(v[4 * j], 0.f), u1 = fmaxf(v[4 * j + 1], 0.f), u2 = fmaxf(v[4 * j + 2], 0.f),
                     u3 = fmaxf(v[4 * j + 3], 0.f);
         c0 = fmaf(u0, w0.x, fmaf(u1, w0.y, fmaf(u2, w0.z, fmaf(u3, w0.w, c0))));
@@ -271,36 +309,26 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
       }
     }
   }
-  // ---- heads: the two column halves of a row live in warps w and w+8; combine through shared memory ----
-  if (KIND == EPI_RELU_SIGMA) {
-    if (half == 1) asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + row * 4), "f"(sig_acc) : "memory");
+  // ---- heads: the two column halves of a row live in warps w and w+8 (same TMEM lanes).  The upper half parks its
+  // partial sums in accumulator columns it has already drained; the lower half picks them up after a 64-thread
+  // named barrier.  Nothing overwrites those columns before both halves arrive on act_ready.
+  if (KIND == EPI_RELU_SIGMA || KIND == EPI_COLOUR) {
+    const uint32_t park = tmem_row + (KIND == EPI_COLOUR ? 64 : 128);
+    if (half == 1) tmem_st4(park, sig_acc, c0, c1, c2);
+    tc_fence_before();
     asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    tc_fence_after();
     if (half == 0) {
-      float other;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(scratch + row * 4) : "memory");
-      if (valid) P.sigma[s] = fabsf(sig_acc + other + __ldg(aux + AUX_SIG_B));
-    }
-  }
-  if (KIND == EPI_COLOUR) {
-    // the view-feature tile is free (every MMA of this pair has retired): use its first 2 KB as scratch
-    if (half == 1)
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(enc + row * 16), "f"(c0), "f"(c1), "f"(c2), "f"(0.f)
-                   : "memory");
-    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-    if (half == 0) {
-      float o0, o1, o2, o3;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(o0), "=f"(o1), "=f"(o2), "=f"(o3)
-                   : "r"(enc + row * 16)
-                   : "memory");
-      if (valid) {
-        P.rgb[s * 3 + 0] = 1.f / (1.f + __expf(-(c0 + o0 + __ldg(aux + AUX_COL_B))));
-        P.rgb[s * 3 + 1] = 1.f / (1.f + __expf(-(c1 + o1 + __ldg(aux + AUX_COL_B + 1))));
-        P.rgb[s * 3 + 2] = 1.f / (1.f + __expf(-(c2 + o2 + __ldg(aux + AUX_COL_B + 2))));
+      float o_s, o0, o1, o2;
+      tmem_ld4(park, o_s, o0, o1, o2);
+      if (KIND == EPI_RELU_SIGMA) {
+        if (valid) P.sigma[s] = fabsf(sig_acc + o_s + lds32(aux_s + AUX_SIG_B * 4));
+      } else if (valid) {
+        P.rgb[s * 3 + 0] = 1.f / (1.f + __expf(-(c0 + o0 + lds32(aux_s + AUX_COL_B * 4))));
+        P.rgb[s * 3 + 1] = 1.f / (1.f + __expf(-(c1 + o1 + lds32(aux_s + AUX_COL_B * 4 + 4))));
+        P.rgb[s * 3 + 2] = 1.f / (1.f + __expf(-(c2 + o2 + lds32(aux_s + AUX_COL_B * 4 + 8))));
       }
     }
-    // the next pair's encoder overwrites this scratch: make sure the reader is done first
-    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
   }
 }
 
@@ -314,7 +342,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = sbase + OFF_BAR;
   auto bar = [&](int i) { return bar0 + 8u * i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 96);
 
   if (threadIdx.x == 0) {
     if (sbase & 1023) __trap();  // SWIZZLE_128B operands need a 1024-byte aligned base
@@ -326,6 +354,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
       mbar_init(bar(BAR_ACC_FULL + tl), 1);
       mbar_init(bar(BAR_ACT_READY + tl), 2 * TILE_M);
     }
+    mbar_init(bar(BAR_AUX_FULL), 1);
     fence_mbar_init();
   }
   if (warp == WARP_MMA) tmem_alloc_512(smem_u32(tmem_slot));
@@ -356,7 +385,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
     // ===================== MMA issuer: one thread drives the tensor core for both tiles =====================
     if (lane == 0) {
       uint32_t q = 0, lit = 0;
-      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
+      int pair_local = 0;
+      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pair_local) {
         for (int L = 0; L < N_MMA_LAYERS; ++L, ++lit) {
           const int nch = layer_chunks(L);
           const uint32_t idesc = umma_idesc(layer_n(L));
@@ -370,6 +400,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
               if (kc == 0) {  // A operand written + accumulator drained by the tile's epilogue warps
                 mbar_wait(bar(BAR_ACT_READY + tl), lit & 1);
                 tc_fence_after();
+                TC_PROF(tl);
+                if (tl == 1) {
+                  // every epilogue thread is done with the previous layer's record: stage this layer's biases / head
+                  // weights (1-2.5 KB) for the epilogue that follows these MMAs
+                  mbar_expect_tx(bar(BAR_AUX_FULL), aux_bytes(L));
+                  tma_bulk_g2s(sbase + OFF_AUX, P.packed + PACKED_W_BYTES + L * (AUX_REC_FLOATS * 4), aux_bytes(L),
+                               bar(BAR_AUX_FULL));
+                }
               }
               const bool from_enc = (L == 0) || (kc == 4);
               const uint32_t a_addr = from_enc ? sbase + OFF_ENC + tl * CHUNK_A_BYTES
@@ -381,6 +419,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
               if (kc == nch - 1) umma_commit(bar(BAR_ACC_FULL + tl));
             }
             umma_commit(bar(BAR_W_EMPTY + stage));  // frees the ring slot once both tiles' MMAs retire
+            if (kc == 0) TC_PROF(2);
+            if (kc == nch - 1) TC_PROF(3);
           }
         }
       }
@@ -393,14 +433,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
     const int pair_bar = 1 + (warp & 7);  // named barrier shared by the two warps that own the same rows
     const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
     const uint32_t enc = sbase + OFF_ENC + tl * CHUNK_A_BYTES;
-    const uint32_t scratch = sbase + OFF_SCRATCH + tl * TILE_M * 4;
+    const uint32_t aux_s = sbase + OFF_AUX;
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + tl * 256;
-    const float* __restrict__ aux = reinterpret_cast<const float*>(P.packed + PACKED_W_BYTES);
     RowSwz sw;
     sw.row_off = row * 128;
     sw.x4 = (row & 7) << 4;
     uint32_t it = 0;
-    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
+    int pair_local = 0;
+    const int pslot = 4 + 3 * (warp >> 2);  // per warp-group stamp slots (lane 0 of warps 0, 4, 8, 12)
+    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pair_local) {
       const int64_t s = ((int64_t)pair * 2 + tl) * TILE_M + row;
       const bool valid = s < P.total;
       const int64_t sc = valid ? s : P.total - 1;
@@ -441,14 +482,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
       for (int L = 0; L < N_MMA_LAYERS; ++L, ++it) {
         mbar_wait(bar(BAR_ACC_FULL + tl), it & 1);
         tc_fence_after();
+        mbar_wait(bar(BAR_AUX_FULL), it & 1);
+        if ((warp & 3) == 0 && lane == 0) TC_PROF(pslot);
         if (L == 7)
-          epilogue_layer<EPI_RELU_SIGMA, DBG>(P, L, half, tmem_row, act, scratch, enc, pair_bar, sw, row, aux, s, valid);
+          epilogue_layer<EPI_RELU_SIGMA, DBG>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
         else if (L == 8)
-          epilogue_layer<EPI_LINEAR, DBG>(P, L, half, tmem_row, act, scratch, enc, pair_bar, sw, row, aux, s, valid);
+          epilogue_layer<EPI_LINEAR, DBG>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
         else if (L == 9)
-          epilogue_layer<EPI_COLOUR, DBG>(P, L, half, tmem_row, act, scratch, enc, pair_bar, sw, row, aux, s, valid);
+          epilogue_layer<EPI_COLOUR, DBG>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
         else
-          epilogue_layer<EPI_RELU, DBG>(P, L, half, tmem_row, act, scratch, enc, pair_bar, sw, row, aux, s, valid);
+          epilogue_layer<EPI_RELU, DBG>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
         if (L == 4) {
           // all MMAs that read the xyz features have retired: reuse the tile for the view-direction features
           // (24 features = 16-byte chunks 0-2 by half 0; zero chunks 3-7 split between the halves)
@@ -469,11 +512,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
             for (int j = 4; j < 8; ++j) st_shared_v4(sw.addr(enc, j), 0u, 0u, 0u, 0u);
           }
         }
+        if ((warp & 3) == 0 && lane == 0) TC_PROF(pslot + 1);
         if (L != 9) {
           fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
           tc_fence_before();
           mbar_arrive(bar(BAR_ACT_READY + tl));
         }
+        if ((warp & 3) == 0 && lane == 0) TC_PROF(pslot + 2);
       }
     }
   }
@@ -506,17 +551,17 @@ __global__ void pack_weights_kernel(const float* __restrict__ params, uint8_t* _
     const int a = gid - PACKED_W_BYTES / 16;
     if (a >= AUX_FLOATS) return;
     float v = 0.f;
-    if (a < AUX_SIG_W) {
-      const int L = a / 256, i = a % 256;
-      v = i < layer_n(L) ? params[pp.bias_off[L] + i] : 0.f;
-    } else if (a < AUX_COL_W)
-      v = params[pp.sig_w + (a - AUX_SIG_W)];
-    else if (a < AUX_SIG_B)
-      v = params[pp.col_w + (a - AUX_COL_W)];
-    else if (a == AUX_SIG_B)
+    const int L = a / AUX_REC_FLOATS, i = a % AUX_REC_FLOATS;
+    if (i < layer_n(L))
+      v = params[pp.bias_off[L] + i];
+    else if (L == 9 && i >= AUX_COL_B && i < AUX_COL_B + 3)
+      v = params[pp.col_b + (i - AUX_COL_B)];
+    else if (L == 7 && i >= AUX_EXTRA && i < AUX_EXTRA + 256)
+      v = params[pp.sig_w + (i - AUX_EXTRA)];
+    else if (L == 7 && i == AUX_SIG_B)
       v = params[pp.sig_b];
-    else if (a < AUX_COL_B + 3)
-      v = params[pp.col_b + (a - AUX_COL_B)];
+    else if (L == 9 && i >= AUX_EXTRA)
+      v = params[pp.col_w + (i - AUX_EXTRA)];
     reinterpret_cast<float*>(packed + PACKED_W_BYTES)[a] = v;
     return;
   }
