@@ -105,6 +105,12 @@ int nt_mlp_forward_debug(nt_ctx* ctx, int64_t n, int p, const float* t, const fl
                          const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int layer,
                          void* stream);
 
+/* Diagnostic: the bf16 tensor-core GEMM used by the NT_PREC_BF16 training path.  mn_major = 0: a [M][K], b [N][K];
+ * 1: a [K][M], b [K][N] (bf16, K multiple of 64, N <= 256).  out_f32 = 0: c bf16 [M][ldc] (optionally masked by
+ * mask > 0, bf16 [M][ldmask]); 1: fp32 atomically accumulated into c [M][ldc]. */
+int nt_gemm_bf16_debug(nt_ctx* ctx, int mn_major, int m, int n, int k, const void* a, int lda, const void* b, int ldb,
+                       void* c, int ldc, int out_f32, const void* mask, int ldmask, void* stream);
+
 /* ---- compositing: get_density nerf.py:263-272 + color_cum nerf.py:274-281 ----------------
  * coarse: delta = (far-near)/Nc for every sample (nerf.py:293).  weights dev [N,Nc], c_out dev [N,3]. */
 int nt_composite_coarse(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, const float* rgb,

@@ -264,3 +264,18 @@ extern "C" int nt_mlp_forward_debug(nt_ctx* ctx, int64_t n, int p, const float* 
   if (n <= 0) return NT_OK;
   return nt_mlp_tc_forward_dbg(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, dbg, layer, (cudaStream_t)stream);
 }
+
+// diagnostic: raw bf16 tensor-core GEMM (gemm_tc.cu) for the unit tests.  mn_major = 0: A [M][K], B [N][K];
+// 1: A [K][M], B [K][N].  out_f32 = 0: C bf16 [M][ldc]; 1: fp32 atomically accumulated into C.
+extern "C" int nt_gemm_bf16_debug(nt_ctx* ctx, int mn_major, int m, int n, int k, const void* a, int lda, const void* b,
+                                  int ldb, void* c, int ldc, int out_f32, const void* mask, int ldmask, void* stream) {
+  NT_REQUIRE(ctx && a && b && c, "null pointer");
+  GemmTcEpi e;
+  memset(&e, 0, sizeof(e));
+  e.C = c;
+  e.ldc = ldc;
+  e.atomic_f32 = out_f32;
+  e.mask = mask;
+  e.ldmask = ldmask;
+  return nt_launch_gemm_tc(ctx, mn_major, m, n, k, a, lda, b, ldb, e, (cudaStream_t)stream);
+}

@@ -127,3 +127,19 @@ int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const f
 int nt_launch_composite_fine_fwd(nt_ctx* ctx, int64_t n, const float* t_c, const float* rgb_c, const float* sigma_c,
                                  const float* t_f, const float* rgb_f, const float* sigma_f, float last, float* c_out,
                                  float* weights, uint8_t* perm, cudaStream_t st);
+
+// gemm_tc.cu — bf16 tcgen05 GEMM (training path)
+struct GemmTcEpi {
+  void* C;            // bf16 [M][ldc] (store) or fp32 [M][ldc] (atomic_f32 / store_f32)
+  int ldc;
+  int atomic_f32;     // fp32 vector atomics (split-K weight gradients, fp32 accumulation into an existing buffer)
+  int store_f32;      // plain fp32 store
+  const float* bias;  // [N] or null
+  int relu;
+  const void* mask;   // bf16 [M][ldmask] or null: out = mask > 0 ? v : 0
+  int ldmask;
+  const float* r1_row;  // optional rank-1 term added before the mask: v += r1_row[m] * r1_col[n]
+  const float* r1_col;
+};
+int nt_launch_gemm_tc(nt_ctx* ctx, int mn_major, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                      const GemmTcEpi& epi, cudaStream_t st);

@@ -1,0 +1,469 @@
+// Generic bf16 tcgen05 GEMM with fp32 accumulation in TMEM — the backbone of the NT_PREC_BF16 training path
+// (autograd of Network.forward, nerf.py:101-124 / loss.backward() nerf.py:473).
+//
+//   D[M, N] = A (.) B          M = rows of the CTA tile (128), N = BN (64 | 128 | 256), K streamed in 64-wide blocks
+//   K_MAJOR : A stored [M][K], B stored [N][K]           (dX = G . W : B is the pre-transposed weight)
+//   MN_MAJOR: A stored [K][M], B stored [K][N]           (dW = G^T . H : K is the SAMPLE axis, split over CTAs)
+// Operands are fetched with TMA tensor maps (cp.async.bulk.tensor, SWIZZLE_128B) into a 4-stage mbarrier ring by
+// one producer warp; one elected thread issues tcgen05.mma (M=128, N=BN, K=16); two TMEM accumulator stages let the
+// 8 epilogue warps drain tile i while tile i+1 is being multiplied.  With b_resident the (small) B operand is loaded
+// once per CTA and kept in shared memory while M-tiles of A stream past it.
+// Epilogues: bf16 store with optional bias / ReLU / ReLU'-mask (mask = stored activation > 0), or fp32 vector
+// atomics (split-K weight gradients).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int NSTAGE = 4;
+constexpr int A_STAGE_BYTES = BM * 128;
+constexpr int GEMM_THREADS = 320;  // warp 0 = TMA, warp 1 = MMA, warps 2-9 = epilogue
+
+struct GemmTcArgs {
+  int M, N, K;        // problem (N <= BN, one N tile)
+  int n_valid;        // columns actually written (<= N)
+  int split_k;        // CTAs along K (atomic epilogue only)
+  int kb_per_split;   // 64-wide K blocks per split
+  int b_resident;     // keep all K blocks of B in smem (requires K <= NSTAGE*64, split_k == 1)
+  int epi;            // 0 = bf16 store, 1 = fp32 atomic add, 2 = fp32 store
+  void* C;
+  int ldc;
+  const float* bias;  // [N] or null (bf16 store only)
+  int relu;
+  const __nv_bfloat16* mask;  // [M][ldmask] or null: out = mask > 0 ? acc : 0
+  int ldmask;
+  const float* r1_row;  // rank-1 term v += r1_row[m] * r1_col[n] (sigma-head gradient joining point_info's)
+  const float* r1_col;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins == 1024) t0 = clock64();
+    if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();  // never hang the GPU
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+// K-major SW128 descriptor (8-row groups 1024 B apart) / MN-major SW128 descriptor (64-element MN blocks `lbo` bytes
+// apart, 8-row K groups 1024 B apart) — cute::UMMA::SmemDescriptor bit layout
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int n, bool mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (1u << 15) | (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <int BN, bool MN_MAJOR>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmTcArgs g) {
+  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int OFF_A = 0;
+  constexpr int OFF_B = NSTAGE * A_STAGE_BYTES;
+  constexpr int OFF_BAR = OFF_B + NSTAGE * B_STAGE_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // barriers: full[4] 0-3, empty[4] 4-7, acc_full[2] 8-9, acc_empty[2] 10-11, b_full 12
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 112);
+
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const int kb_total = g.K / BK;
+  const int items = m_tiles * g.split_k;
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023) __trap();
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bar(s), 1);
+      mbar_init(bar(4 + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(8 + s), 1);
+      mbar_init(bar(10 + s), 256);
+    }
+    mbar_init(bar(12), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      uint32_t q = 0;  // ring counter
+      bool b_loaded = false;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int mt = item % m_tiles, sp = item / m_tiles;
+        const int kb0 = sp * g.kb_per_split;
+        const int kb1 = min(kb_total, kb0 + g.kb_per_split);
+        if (g.b_resident && !b_loaded) {
+          mbar_expect_tx(bar(12), kb_total * B_STAGE_BYTES);
+          for (int kb = 0; kb < kb_total; ++kb) {
+            const uint32_t dst = sbase + OFF_B + kb * B_STAGE_BYTES;
+            if (MN_MAJOR) {
+              for (int b = 0; b < BN / 64; ++b) tma_load_2d(dst + b * 8192, &map_b, b * 64, kb * BK, bar(12));
+            } else {
+              tma_load_2d(dst, &map_b, kb * BK, 0, bar(12));
+            }
+          }
+          b_loaded = true;
+        }
+        for (int kb = kb0; kb < kb1; ++kb, ++q) {
+          const uint32_t s = q % NSTAGE;
+          mbar_wait(bar(4 + s), ((q / NSTAGE) & 1) ^ 1);
+          mbar_expect_tx(bar(s), A_STAGE_BYTES + (g.b_resident ? 0 : B_STAGE_BYTES));
+          const uint32_t da = sbase + OFF_A + s * A_STAGE_BYTES;
+          if (MN_MAJOR) {
+            tma_load_2d(da, &map_a, mt * BM, kb * BK, bar(s));
+            tma_load_2d(da + 8192, &map_a, mt * BM + 64, kb * BK, bar(s));
+          } else {
+            tma_load_2d(da, &map_a, kb * BK, mt * BM, bar(s));
+          }
+          if (!g.b_resident) {
+            const uint32_t db = sbase + OFF_B + s * B_STAGE_BYTES;
+            if (MN_MAJOR) {
+              for (int b = 0; b < BN / 64; ++b) tma_load_2d(db + b * 8192, &map_b, b * 64, kb * BK, bar(s));
+            } else {
+              tma_load_2d(db, &map_b, kb * BK, 0, bar(s));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(BN, MN_MAJOR);
+      uint32_t q = 0, it = 0;
+      bool b_ready = false;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const int sp = item / m_tiles;
+        const int kb0 = sp * g.kb_per_split;
+        const int kb1 = min(kb_total, kb0 + g.kb_per_split);
+        const uint32_t as = it & 1;  // accumulator stage
+        mbar_wait(bar(10 + as), ((it >> 1) & 1) ^ 1);  // epilogue drained this TMEM stage
+        tc_fence_after();
+        if (g.b_resident && !b_ready) {
+          mbar_wait(bar(12), 0);
+          b_ready = true;
+        }
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int kb = kb0; kb < kb1; ++kb, ++q) {
+          const uint32_t s = q % NSTAGE;
+          mbar_wait(bar(s), (q / NSTAGE) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = sbase + OFF_A + s * A_STAGE_BYTES;
+          const uint32_t b_addr = sbase + OFF_B + (g.b_resident ? kb : s) * B_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint64_t ad, bd;
+            if (MN_MAJOR) {  // 16 K-rows = 2 KB per step inside each 64-element MN block (blocks 8 KB apart)
+              ad = desc_mnmajor(a_addr + j * 2048, 8192);
+              bd = desc_mnmajor(b_addr + j * 2048, 8192);
+            } else {
+              ad = desc_kmajor(a_addr + j * 32);
+              bd = desc_kmajor(b_addr + j * 32);
+            }
+            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(bar(4 + s));
+        }
+        umma_commit(bar(8 + as));
+      }
+    }
+  } else {
+    // ======================= epilogue: 8 warps = 4 lane quadrants x 2 column halves =======================
+    const int e = warp - 2;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access (warp id % 4)
+    const int half = e >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    constexpr int NCB = BN / 64;  // 32-column blocks per half
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int mt = item % m_tiles;
+      const uint32_t as = it & 1;
+      mbar_wait(bar(8 + as), (it >> 1) & 1);
+      tc_fence_after();
+      const int m = mt * BM + row_in_tile;
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
+#pragma unroll
+      for (int i = 0; i < NCB; ++i) {
+        const int n0 = (half * NCB + i) * 32;
+        uint32_t raw[32];
+        tmem_ld32(trow + n0, raw);
+        if (m < g.M && n0 < g.n_valid) {
+          if (g.epi == 1) {
+            float* c = reinterpret_cast<float*>(g.C) + (int64_t)m * g.ldc + n0;
+            if (n0 + 32 <= g.n_valid && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4 * j), "f"(__uint_as_float(raw[4 * j])),
+                             "f"(__uint_as_float(raw[4 * j + 1])), "f"(__uint_as_float(raw[4 * j + 2])),
+                             "f"(__uint_as_float(raw[4 * j + 3]))
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.n_valid) atomicAdd(c + j, __uint_as_float(raw[j]));
+            }
+          } else {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+            if (g.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(g.bias + n0 + j);
+            }
+            if (g.r1_row) {
+              const float rr = __ldg(g.r1_row + m);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaf(rr, __ldg(g.r1_col + n0 + j), v[j]);
+            }
+            if (g.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (g.mask && ((reinterpret_cast<uintptr_t>(g.mask + (int64_t)m * g.ldmask + n0) & 15) != 0 || n0 + 32 > g.n_valid)) {
+              const __nv_bfloat16* mk = g.mask + (int64_t)m * g.ldmask + n0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.n_valid && !(__bfloat162float(mk[j]) > 0.f)) v[j] = 0.f;
+            } else if (g.mask) {
+              const uint4* mk = reinterpret_cast<const uint4*>(g.mask + (int64_t)m * g.ldmask + n0);
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) {
+                const uint4 mm = __ldg(mk + qd);
+                const uint32_t w[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) {
+                  // bf16 > 0  <=>  sign clear and not zero
+                  const uint32_t lo = w[k2] & 0xffffu, hi = w[k2] >> 16;
+                  if (!(lo != 0 && lo < 0x8000u)) v[qd * 8 + k2 * 2] = 0.f;
+                  if (!(hi != 0 && hi < 0x8000u)) v[qd * 8 + k2 * 2 + 1] = 0.f;
+                }
+              }
+            }
+            if (g.epi == 2) {
+              float* cf = reinterpret_cast<float*>(g.C) + (int64_t)m * g.ldc + n0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.n_valid) cf[j] = v[j];
+              continue;
+            }
+            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(g.C) + (int64_t)m * g.ldc + n0;
+            if (n0 + 32 <= g.n_valid && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd)
+                *reinterpret_cast<uint4*>(c + qd * 8) =
+                    make_uint4(pack2(v[qd * 8], v[qd * 8 + 1]), pack2(v[qd * 8 + 2], v[qd * 8 + 3]),
+                               pack2(v[qd * 8 + 4], v[qd * 8 + 5]), pack2(v[qd * 8 + 6], v[qd * 8 + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.n_valid) c[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar(10 + as));
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- host side: tensor maps ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows][cols] (cols contiguous, row pitch ld elements); box = box_cols x box_rows, SWIZZLE_128B
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    nt_set_error("cuTensorMapEncodeTiled entry point not available");
+    return NT_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    nt_set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box=%dx%d base=%p", (int)r, (long long)rows,
+                 (long long)cols, (long long)ld, box_cols, box_rows, base);
+    return NT_ERR_CUDA;
+  }
+  return NT_OK;
+}
+
+template <int BN, bool MN>
+int launch(nt_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const GemmTcArgs& g, cudaStream_t st) {
+  constexpr int smem = NSTAGE * A_STAGE_BYTES + NSTAGE * BN * 128 + 128;
+  static bool set = false;
+  if (!set) {
+    NT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    set = true;
+  }
+  const int items = ((g.M + BM - 1) / BM) * g.split_k;
+  const int grid = items < ctx->sm_count ? items : ctx->sm_count;
+  gemm_tc_kernel<BN, MN><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, g);
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
+
+}  // namespace
+
+// C = A (.) B with bf16 operands.  mn_major = 0: A [M][K] (lda), B [N][K] (ldb); 1: A [K][M] (lda), B [K][N] (ldb).
+// N is rounded up to 64/128/256 internally (TMA zero-fills out-of-range rows/cols); n_valid columns are written.
+int nt_launch_gemm_tc(nt_ctx* ctx, int mn_major, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                      const GemmTcEpi& epi, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return NT_OK;
+  if (K % BK != 0 || N > 256) {
+    nt_set_error("gemm_tc: K must be a multiple of 64 and N <= 256 (K=%d N=%d)", K, N);
+    return NT_ERR_INVALID;
+  }
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  GemmTcArgs g;
+  g.M = M;
+  g.N = BN;
+  g.K = K;
+  g.n_valid = N;
+  g.epi = epi.atomic_f32 ? 1 : (epi.store_f32 ? 2 : 0);
+  g.r1_row = epi.r1_row;
+  g.r1_col = epi.r1_col;
+  g.C = epi.C;
+  g.ldc = epi.ldc;
+  g.bias = epi.bias;
+  g.relu = epi.relu;
+  g.mask = reinterpret_cast<const __nv_bfloat16*>(epi.mask);
+  g.ldmask = epi.ldmask;
+  const int kb_total = K / BK;
+  const int m_tiles = (M + BM - 1) / BM;
+  g.split_k = 1;
+  if (epi.atomic_f32) {
+    int want = (2 * ctx->sm_count) / (m_tiles > 0 ? m_tiles : 1);
+    if (want < 1) want = 1;
+    if (want > kb_total) want = kb_total;
+    g.split_k = want;
+  }
+  g.kb_per_split = (kb_total + g.split_k - 1) / g.split_k;
+  g.split_k = (kb_total + g.kb_per_split - 1) / g.kb_per_split;
+  g.b_resident = (!epi.atomic_f32 && kb_total <= NSTAGE && m_tiles > ctx->sm_count) ? 1 : 0;
+  CUtensorMap ma, mb;
+  int rc;
+  if (mn_major) {
+    if ((rc = make_map(&ma, A, K, M, lda, 64, BK)) != NT_OK) return rc;
+    if ((rc = make_map(&mb, B, K, N, ldb, 64, BK)) != NT_OK) return rc;
+  } else {
+    if ((rc = make_map(&ma, A, M, K, lda, BK, BM)) != NT_OK) return rc;
+    if ((rc = make_map(&mb, B, N, K, ldb, BK, BN)) != NT_OK) return rc;
+  }
+  if (mn_major) {
+    if (BN == 64) return launch<64, true>(ctx, ma, mb, g, st);
+    if (BN == 128) return launch<128, true>(ctx, ma, mb, g, st);
+    return launch<256, true>(ctx, ma, mb, g, st);
+  }
+  if (BN == 64) return launch<64, false>(ctx, ma, mb, g, st);
+  if (BN == 128) return launch<128, false>(ctx, ma, mb, g, st);
+  return launch<256, false>(ctx, ma, mb, g, st);
+}

@@ -250,16 +250,18 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
   constexpr int NCB = KIND == EPI_COLOUR ? 2 : 4;  // 32-column blocks per half
   const int cb0 = half * NCB;
   float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  uint32_t buf[2][32];  // double-buffered accumulator blocks: the next TMEM load is in flight during the math
+  tmem_ld32_issue(tmem_row + cb0 * 32, buf[0]);
 #pragma unroll
   for (int i = 0; i < NCB; ++i) {
     const int cb = cb0 + i;
-    uint32_t raw[32];
-    tmem_ld32_issue(tmem_row + cb * 32, raw);
+    uint32_t(&raw)[32] = buf[i & 1];
+    tmem_ld_wait(raw);
+    if (i + 1 < NCB) tmem_ld32_issue(tmem_row + (cb + 1) * 32, buf[(i + 1) & 1]);
     const uint32_t bias_s = aux_s + cb * 128;
     float4 b4[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) b4[j] = lds128(bias_s + j * 16);
-    tmem_ld_wait(raw);
     float v[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
