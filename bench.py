@@ -352,9 +352,11 @@ def bench_train(model, dev, rows17, world, rank, barrier, args):
     model.eval()
     v = world * TRAIN_BATCH / (ms * 1e-3)
     return {"metric": "rays/sec (train step: fwd+bwd+Adam, coarse64+fine128)", "value": v, "unit": "rays/s",
-            "ms_per_step": ms, "rays_per_step_per_gpu": TRAIN_BATCH, "steps": steps, "dtype": "f32",
-            "note": "training runs the fp32 layer-major kernels this round (tcgen05 backward: next round); "
-                    "host batches, H2D inside the timed region; one SUM all-reduce of the 2.4 MB gradient per step when N>1",
+            "ms_per_step": ms, "rays_per_step_per_gpu": TRAIN_BATCH, "steps": steps,
+            "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "note": "fused tcgen05 forward with bf16 activation stash + layer-major tcgen05 backward (dX / split-K dW GEMMs) "
+                    "+ fused Adam; host batches, H2D inside the timed region; one SUM all-reduce of the 2.4 MB gradient "
+                    "per step when N>1",
             "frac_of_tc_peak": v / world * FLOP_PER_RAY_TRAIN / (peaks()["tf"] * 1e12), "last_loss": float(loss)}
 
 

@@ -35,6 +35,7 @@ SIGNATURES = {
     "nt_param_count": (i64, []),
     "nt_layer_table": (i32, [C.POINTER(LayerDesc)]),
     "nt_launch_count": (i64, [vp]),
+    "nt_set_option": (i32, [vp, i32, i32]),
     "nt_raygen": (i32, [vp, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     "nt_sample_coarse": (i32, [vp, i64, vp, vp, i32, vp, vp]),
     "nt_mlp_workspace_bytes": (sz, [vp, i32, i64, i32, i32]),

@@ -56,6 +56,7 @@ extern "C" int nt_create(nt_ctx** out, int device, int n_coarse, int n_fine) {
   c->n_fine = n_fine;
   c->sm_count = prop.multiProcessorCount;
   c->launches = 0;
+  c->opt_detach_t_fine = 0;
   c->d_flags = nullptr;
   if (cudaMalloc(&c->d_flags, 4 * sizeof(int)) != cudaSuccess || cudaMemset(c->d_flags, 0, 4 * sizeof(int)) != cudaSuccess) {
     nt_set_error("cudaMalloc of the status flags failed");
@@ -74,11 +75,21 @@ extern "C" void nt_destroy(nt_ctx* ctx) {
 
 extern "C" int64_t nt_launch_count(const nt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int nt_set_option(nt_ctx* ctx, int key, int value) {
+  NT_REQUIRE(ctx, "null ctx");
+  if (key == NT_OPT_DETACH_T_FINE) {
+    ctx->opt_detach_t_fine = value != 0;
+    return NT_OK;
+  }
+  nt_set_error("unknown option %d", key);
+  return NT_ERR_INVALID;
+}
+
 // ---- precision dispatch ------------------------------------------------------------------------
 extern "C" size_t nt_mlp_workspace_bytes(nt_ctx* ctx, int precision, int64_t n, int p, int train) {
   (void)ctx;
   if (precision == NT_PREC_FP32) return nt_mlp_f32_workspace_bytes(n, p, train);
-  if (precision == NT_PREC_BF16) return train ? nt_mlp_f32_workspace_bytes(n, p, 1) : 256;
+  if (precision == NT_PREC_BF16) return train ? nt_mlp_bf16_train_workspace_bytes(n, p) : 256;
   return 0;
 }
 extern "C" size_t nt_packed_weight_bytes(nt_ctx* ctx, int precision) {
@@ -98,13 +109,17 @@ extern "C" int nt_mlp_forward(nt_ctx* ctx, int precision, int64_t n, int p, cons
   NT_REQUIRE(ctx && t && rays && dir_enc && params && rgb && sigma, "null pointer");
   NT_REQUIRE(p > 0 && n >= 0, "bad shape");
   if (n == 0) return NT_OK;
-  if (precision == NT_PREC_FP32 || (precision == NT_PREC_BF16 && train)) {
-    // training keeps fp32 activations for the layer-major backward (bf16 training kernels: next round)
+  if (precision == NT_PREC_FP32) {
     NT_REQUIRE(ws, "fp32 MLP needs a workspace");
     return nt_mlp_f32_forward(ctx, n, p, t, rays, dir_enc, params, rgb, sigma, ws, ws_bytes, train, (cudaStream_t)stream);
   }
   if (precision == NT_PREC_BF16) {
     NT_REQUIRE(packed, "NT_PREC_BF16 needs packed weights (nt_pack_weights)");
+    if (train) {  // fused tcgen05 forward + bf16 activation stash for the tensor-core backward
+      NT_REQUIRE(ws, "bf16 training needs a workspace");
+      return nt_mlp_bf16_train_forward(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, ws, ws_bytes,
+                                       (cudaStream_t)stream);
+    }
     return nt_mlp_tc_forward(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, (cudaStream_t)stream);
   }
   nt_set_error("unknown precision %d", precision);
@@ -119,6 +134,9 @@ extern "C" int nt_mlp_backward(nt_ctx* ctx, int precision, int64_t n, int p, con
   NT_REQUIRE(ctx && t && rays && params && g_rgb && g_sigma && grads && ws, "null pointer");
   NT_REQUIRE(precision == NT_PREC_FP32 || precision == NT_PREC_BF16, "unknown precision");
   if (n == 0) return NT_OK;
+  if (precision == NT_PREC_BF16)
+    return nt_mlp_bf16_train_backward(ctx, n, p, t, rays, params, nullptr, g_rgb, g_sigma, grads, g_t, ws, ws_bytes,
+                                      (cudaStream_t)stream);
   return nt_mlp_f32_backward(ctx, n, p, t, rays, params, g_rgb, g_sigma, grads, g_t, ws, ws_bytes, (cudaStream_t)stream);
 }
 
@@ -226,16 +244,19 @@ extern "C" int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const f
   NT_TRY(nt_composite_fine_backward(ctx, n, w.t_c, w.rgb_c, w.sig_c, w.t_f, w.rgb_f, w.sig_f, 1e-4f, w.perm, g_c_fine,
                                     w.g_rgb_c, w.g_sig_c, w.g_rgb_f, w.g_sig_f, w.g_t_f, stream));
   // fine MLP: dW + input gradient down to t_fine (B.4, B.6, B.7)
+  const bool detach = ctx->opt_detach_t_fine != 0;
   NT_TRY(nt_mlp_backward(ctx, precision, n, nf, w.t_f, w.rays, w.dir_enc, params, packed, w.g_rgb_f, w.g_sig_f, grads,
-                         w.g_t_mlp, w.mlp_f, w.mlp_f_bytes, stream));
+                         detach ? nullptr : w.g_t_mlp, w.mlp_f, w.mlp_f_bytes, stream));
   // g_t_fine = compositing path + MLP-input path; then resample backward (B.5)
-  NT_TRY(nt_launch_axpy(ctx, n * nf, w.g_t_mlp, w.g_t_f, (cudaStream_t)stream));
-  NT_TRY(nt_sample_pdf_backward(ctx, n, w.t_c, w.w_c, delta0, w.g_t_f, w.g_w_c, stream));
+  if (!detach) {
+    NT_TRY(nt_launch_axpy(ctx, n * nf, w.g_t_mlp, w.g_t_f, (cudaStream_t)stream));
+    NT_TRY(nt_sample_pdf_backward(ctx, n, w.t_c, w.w_c, delta0, w.g_t_f, w.g_w_c, stream));
+  }
   // C_coarse <- composite; rgb/sigma of the coarse samples also feed the fine composite: add both
   float* g_rgb_c2 = w.g_rgb_f;  // fine-pass buffers are free again: reuse as scratch for the coarse composite grads
   float* g_sig_c2 = w.g_sig_f;
-  NT_TRY(nt_composite_coarse_backward(ctx, n, near_, far_, w.rgb_c, w.sig_c, g_c_coarse, w.g_w_c, g_rgb_c2, g_sig_c2,
-                                      stream));
+  NT_TRY(nt_composite_coarse_backward(ctx, n, near_, far_, w.rgb_c, w.sig_c, g_c_coarse, detach ? nullptr : w.g_w_c,
+                                      g_rgb_c2, g_sig_c2, stream));
   NT_TRY(nt_launch_axpy(ctx, n * nc * 3, g_rgb_c2, w.g_rgb_c, (cudaStream_t)stream));
   NT_TRY(nt_launch_axpy(ctx, n * nc, g_sig_c2, w.g_sig_c, (cudaStream_t)stream));
   // coarse MLP: dW only (t_coarse is a constant)

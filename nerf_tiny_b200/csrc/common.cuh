@@ -17,6 +17,7 @@ struct nt_ctx {
   int sm_count;
   int* d_flags;  // [0] = any_step_zero scratch, [1] = resample range status
   int64_t launches;
+  int opt_detach_t_fine;
 };
 
 void nt_set_error(const char* fmt, ...);
@@ -143,3 +144,22 @@ struct GemmTcEpi {
 };
 int nt_launch_gemm_tc(nt_ctx* ctx, int mn_major, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                       const GemmTcEpi& epi, cudaStream_t st);
+
+// bf16 activation stash written by the fused forward (mlp_tc.cu) and consumed by train_bf16.cu
+struct TcStash {
+  void* layer[10];  // bf16 [S][256] for layers 0..8 (h0..h7, point_info), [S][128] for dir_info (u)
+  void* enc;        // bf16 [S][64]
+  void* denc;       // bf16 [S][32]
+  float* zsig;      // fp32 [S]
+};
+int nt_mlp_tc_forward_stash(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                            const float* params, const void* packed, float* rgb, float* sigma, const TcStash* stash,
+                            cudaStream_t st);
+// train_bf16.cu
+size_t nt_mlp_bf16_train_workspace_bytes(int64_t n, int p);
+int nt_mlp_bf16_train_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                              const float* params, const void* packed, float* rgb, float* sigma, void* ws, size_t ws_bytes,
+                              cudaStream_t st);
+int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* params,
+                               const float* rgb, const float* g_rgb, const float* g_sigma, float* grads, float* g_t,
+                               void* ws, size_t ws_bytes, cudaStream_t st);

@@ -14,6 +14,7 @@
 //     sigmoid) are evaluated on CUDA cores from the fp32 accumulators in the same pass.
 // Skip (nerf.py:109) and view (nerf.py:118) concatenations are extra K-chunks accumulated into the same TMEM tile.
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -73,6 +74,11 @@ struct TcParams {
   int64_t total;  // samples
   int p;          // samples per ray
   int num_pairs;
+  // training stash (STASH instantiation): bf16 activations kept in HBM for the layer-major backward
+  __nv_bfloat16* st[N_MMA_LAYERS];  // post-activation output of every tensor-core layer, [S][256] ([S][128] for dir_info)
+  __nv_bfloat16* st_enc;            // xyz features [S][64] (60 + zero pad)
+  __nv_bfloat16* st_denc;           // view features [S][32] (24 + zero pad)
+  float* st_zsig;                   // sigma pre-activation [S] (abs' needs the sign)
 };
 
 __constant__ uint32_t c_tc_freq_point[10] = NT_FREQ_POINT_INIT;
@@ -244,9 +250,10 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float& a, float& b, flo
 // output columns.  accumulator -> +bias -> activation -> bf16 A operand of the next layer (or the heads).
 // 16 epilogue warps (4 per scheduler) hide the TMEM latency by thread-level parallelism; biases and head weights
 // come from the layer's record in shared memory (broadcast LDS, staged by TMA while the MMAs run).
-template <int KIND, bool DBG>
+template <int KIND, bool DBG, bool STASH>
 __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int half, uint32_t tmem_row, uint32_t act,
                                                uint32_t aux_s, int pair_bar, const RowSwz sw, int64_t s, bool valid) {
+  __nv_bfloat16* stp = STASH ? P.st[L] + s * (KIND == EPI_COLOUR ? 128 : 256) : nullptr;
   constexpr int NCB = KIND == EPI_COLOUR ? 2 : 4;  // 32-column blocks per half
   const int cb0 = half * NCB;
   float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
@@ -298,6 +305,13 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
         c1 = fmaf(u0, w1.x, fmaf(u1, w1.y, fmaf(u2, w1.z, fmaf(u3, w1.w, c1))));
         c2 = fmaf(u0, w2.x, fmaf(u1, w2.y, fmaf(u2, w2.z, fmaf(u3, w2.w, c2))));
       }
+      if (STASH && valid) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) =
+              make_uint4(pack_bf16_relu(v[8 * qd], v[8 * qd + 1]), pack_bf16_relu(v[8 * qd + 2], v[8 * qd + 3]),
+                         pack_bf16_relu(v[8 * qd + 4], v[8 * qd + 5]), pack_bf16_relu(v[8 * qd + 6], v[8 * qd + 7]));
+      }
     } else {  // next layer's A operand: K-chunk cb/2, 16-byte chunks (cb%2)*4 .. +3
       const uint32_t dst = act + (cb >> 1) * CHUNK_A_BYTES;
 #pragma unroll
@@ -308,6 +322,7 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
           w[e] = KIND == EPI_LINEAR ? pack_bf16(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1])
                                     : pack_bf16_relu(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1]);
         st_shared_v4(sw.addr(dst, (cb & 1) * 4 + qd), w[0], w[1], w[2], w[3]);
+        if (STASH && valid) *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }
@@ -324,7 +339,9 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
       float o_s, o0, o1, o2;
       tmem_ld4(park, o_s, o0, o1, o2);
       if (KIND == EPI_RELU_SIGMA) {
-        if (valid) P.sigma[s] = fabsf(sig_acc + o_s + lds32(aux_s + AUX_SIG_B * 4));
+        const float z = sig_acc + o_s + lds32(aux_s + AUX_SIG_B * 4);
+        if (valid) P.sigma[s] = fabsf(z);
+        if (STASH && valid) P.st_zsig[s] = z;
       } else if (valid) {
         P.rgb[s * 3 + 0] = 1.f / (1.f + __expf(-(c0 + o0 + lds32(aux_s + AUX_COL_B * 4))));
         P.rgb[s * 3 + 1] = 1.f / (1.f + __expf(-(c1 + o1 + lds32(aux_s + AUX_COL_B * 4 + 4))));
@@ -337,7 +354,7 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
-template <bool DBG>
+template <bool DBG, bool STASH>
 __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -476,6 +493,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           st_shared_v4(sw.addr(enc, half * 4 + j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        if (STASH && valid) {
+          uint4* d = reinterpret_cast<uint4*>(P.st_enc + s * 64 + half * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[j] = make_uint4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
       }
       fence_proxy_async();
       tc_fence_before();
@@ -487,13 +509,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
         mbar_wait(bar(BAR_AUX_FULL), it & 1);
         if ((warp & 3) == 0 && lane == 0) TC_PROF(pslot);
         if (L == 7)
-          epilogue_layer<EPI_RELU_SIGMA, DBG>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
+          epilogue_layer<EPI_RELU_SIGMA, DBG, STASH>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
         else if (L == 8)
-          epilogue_layer<EPI_LINEAR, DBG>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
+          epilogue_layer<EPI_LINEAR, DBG, STASH>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
         else if (L == 9)
-          epilogue_layer<EPI_COLOUR, DBG>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
+          epilogue_layer<EPI_COLOUR, DBG, STASH>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
         else
-          epilogue_layer<EPI_RELU, DBG>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
+          epilogue_layer<EPI_RELU, DBG, STASH>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
         if (L == 4) {
           // all MMAs that read the xyz features have retired: reuse the tile for the view-direction features
           // (24 features = 16-byte chunks 0-2 by half 0; zero chunks 3-7 split between the halves)
@@ -509,6 +531,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
 #pragma unroll
             for (int j = 0; j < 3; ++j) st_shared_v4(sw.addr(enc, j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             st_shared_v4(sw.addr(enc, 3), 0u, 0u, 0u, 0u);
+            if (STASH && valid) {
+              uint4* d = reinterpret_cast<uint4*>(P.st_denc + s * 32);
+#pragma unroll
+              for (int j = 0; j < 3; ++j) d[j] = make_uint4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              d[3] = make_uint4(0u, 0u, 0u, 0u);
+            }
           } else {
 #pragma unroll
             for (int j = 4; j < 8; ++j) st_shared_v4(sw.addr(enc, j), 0u, 0u, 0u, 0u);
@@ -629,16 +657,24 @@ int nt_mlp_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t 
   return NT_OK;
 }
 
-int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
-                          const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int dbg_layer,
-                          cudaStream_t st) {
+static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                         const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int dbg_layer,
+                         const TcStash* stash, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   TcParams P;
+  memset(&P, 0, sizeof(P));
+  if (stash) {
+    for (int i = 0; i < N_MMA_LAYERS; ++i) P.st[i] = (__nv_bfloat16*)stash->layer[i];
+    P.st_enc = (__nv_bfloat16*)stash->enc;
+    P.st_denc = (__nv_bfloat16*)stash->denc;
+    P.st_zsig = stash->zsig;
+  }
   P.t = t;
   P.rays = rays;
   P.dir_enc = dir_enc;
@@ -654,15 +690,27 @@ int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const f
   P.num_pairs = (int)((tiles + 1) / 2);
   if (P.num_pairs == 0) return NT_OK;
   int grid = ctx->sm_count < P.num_pairs ? ctx->sm_count : P.num_pairs;
-  if (dbg)
-    mlp_tc_kernel<true><<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
+  if (stash)
+    mlp_tc_kernel<false, true><<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
+  else if (dbg)
+    mlp_tc_kernel<true, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
   else
-    mlp_tc_kernel<false><<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
+    mlp_tc_kernel<false, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;
 }
 
+int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                          const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int dbg_layer,
+                          cudaStream_t st) {
+  return mlp_tc_launch(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, dbg, dbg_layer, nullptr, st);
+}
 int nt_mlp_tc_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                       const float* params, const void* packed, float* rgb, float* sigma, cudaStream_t st) {
-  return nt_mlp_tc_forward_dbg(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, nullptr, -1, st);
+  return mlp_tc_launch(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, nullptr, -1, nullptr, st);
+}
+int nt_mlp_tc_forward_stash(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                            const float* params, const void* packed, float* rgb, float* sigma, const TcStash* stash,
+                            cudaStream_t st) {
+  return mlp_tc_launch(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, nullptr, -1, stash, st);
 }

@@ -295,6 +295,11 @@ class NeRFModel(nn.Module):
     def check_status(self):
         _lib.check(self._lib.nt_check_status(self._ctx, _stream()))
 
+    def set_detach_t_fine(self, on: bool):
+        """Diagnostic (NT_OPT_DETACH_T_FINE): treat t_fine as a constant in backward.  The reference does not."""
+        self._ensure_ctx()
+        _lib.check(self._lib.nt_set_option(self._ctx, 1, 1 if on else 0))
+
     # -- piecewise methods (same math, single kernels) ---------------------------------------------
     def net_out(self, t_array, batch_x, batch_y, trans_mat, K_inv, num_points):
         """nerf.py:179-222 -> (color [N,P,3], sigma [N,P,1]); no autograd (use forward for training)."""

@@ -194,18 +194,32 @@ def encode(x: torch.Tensor, L: int, faithful32: bool = False) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # a6: the shared MLP (nerf.py:101-124)
 # ---------------------------------------------------------------------------
-def network_forward(sd: Dict[str, torch.Tensor], penc: torch.Tensor, denc: torch.Tensor, return_acts: bool = False):
-    """penc [...,60], denc [...,24] -> color [...,3], sigma [...,1]."""
+def _bf16_st(x: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 with a straight-through gradient (value of bf16(x), derivative of x)."""
+    return x + (x.detach().float().bfloat16().to(x.dtype) - x.detach())
+
+
+def network_forward(sd: Dict[str, torch.Tensor], penc: torch.Tensor, denc: torch.Tensor, return_acts: bool = False,
+                    emulate_bf16: bool = False):
+    """penc [...,60], denc [...,24] -> color [...,3], sigma [...,1].
+    emulate_bf16: model of the NT_PREC_BF16 kernels — the operands of the 10 tensor-core layers (activations and
+    weights) are rounded to bf16, accumulation / biases / the sigma and colour heads stay in the working precision.
+    Its autograd is the exact gradient of that rounded forward, i.e. what the bf16 training path must reproduce."""
+    q = _bf16_st if emulate_bf16 else (lambda x: x)
     acts = []
-    h = penc
+    penc_q = q(penc)
+    h = penc_q
+    pre = None
     for i in range(8):
         k = f"network.point_layer.{i}.0"
-        inp = torch.cat((h, penc), dim=-1) if i == 4 else h   # nerf.py:109 (hidden first)
-        h = torch.relu(F.linear(inp, sd[k + ".weight"], sd[k + ".bias"]))
-        acts.append(h)
-    sigma = torch.abs(F.linear(h, sd["network.sigma_layer.0.weight"], sd["network.sigma_layer.0.bias"]))  # nerf.py:74
-    info = F.linear(h, sd["network.point_info.weight"], sd["network.point_info.bias"])   # nerf.py:117 (no act)
-    u = torch.relu(F.linear(torch.cat((denc, info), dim=-1), sd["network.dir_info.0.weight"],
+        inp = torch.cat((h, penc_q), dim=-1) if i == 4 else h   # nerf.py:109 (hidden first)
+        pre = torch.relu(F.linear(inp, q(sd[k + ".weight"]), sd[k + ".bias"]))
+        h = q(pre)
+        acts.append(pre)
+    # the sigma head reads the un-rounded activations (fp32 accumulator registers in the kernel)
+    sigma = torch.abs(F.linear(pre, sd["network.sigma_layer.0.weight"], sd["network.sigma_layer.0.bias"]))  # nerf.py:74
+    info = F.linear(h, q(sd["network.point_info.weight"]), sd["network.point_info.bias"])   # nerf.py:117 (no act)
+    u = torch.relu(F.linear(torch.cat((q(denc), q(info)), dim=-1), q(sd["network.dir_info.0.weight"]),
                             sd["network.dir_info.0.bias"]))                              # nerf.py:118 (dir first)
     color = torch.sigmoid(F.linear(u, sd["network.color_layer.0.weight"], sd["network.color_layer.0.bias"]))
     if return_acts:
@@ -275,7 +289,7 @@ def merge_sort_composite(t_c, color_c, sigma_c, t_f, color_f, sigma_f, last: flo
 # a13: full forward (nerf.py:286-348)
 # ---------------------------------------------------------------------------
 def net_out(sd, t: torch.Tensor, d_cam: np.ndarray, d_wrd: np.ndarray, c2w: np.ndarray, t_requires_path: bool = False,
-            faithful32: bool = False):
+            faithful32: bool = False, emulate_bf16: bool = False):
     """nerf.py:179-222 for a [N,P] array of t.  If ``t`` carries grad the sample
     positions are rebuilt in torch (p = R*(d_cam*t)+T) so autograd reaches t."""
     n, p = t.shape
@@ -295,12 +309,13 @@ def net_out(sd, t: torch.Tensor, d_cam: np.ndarray, d_wrd: np.ndarray, c2w: np.n
         p32 = sample_points(d_cam.astype(f32), t.detach().float().numpy(), np.asarray(c2w, dtype=f32))
         pts = pts + (torch.from_numpy(p32).double() - pts).detach()
     dirs = torch.from_numpy(d_wrd).to(dt)[:, None, :].expand(n, p, 3)
-    color, sigma = network_forward(sd, encode(pts, 10, faithful32), encode(dirs, 4, faithful32))
+    color, sigma = network_forward(sd, encode(pts, 10, faithful32), encode(dirs, 4, faithful32), emulate_bf16=emulate_bf16)
     return color, sigma.squeeze(-1)
 
 
 def render_rays(sd, row, col, c2w, k_inv, near, far, n_coarse: int = 64, n_fine: int = 128,
-                last: float = 1e-4, return_aux: bool = False, any_step_zero=None, delta0=None):
+                last: float = 1e-4, return_aux: bool = False, any_step_zero=None, delta0=None,
+                detach_t_fine: bool = False, emulate_bf16: bool = False, faithful32: bool = False):
     """nerf.py:286-323.  row/col int arrays [N]; c2w [N,4,4]; near/far [N] (fp32 numpy)."""
     near = np.asarray(near, dtype=f32)
     far = np.asarray(far, dtype=f32)
@@ -310,11 +325,14 @@ def render_rays(sd, row, col, c2w, k_inv, near, far, n_coarse: int = 64, n_fine:
     d_cam, d_wrd = ray_dirs(row, col, np.asarray(k_inv, dtype=f32), c2w, f32=npdt)
     # any_step_zero / delta0: batch-global quantities a ray shard is told explicitly
     t_c = torch.from_numpy(linspace_rows(near, far, n_coarse, any_step_zero=any_step_zero)).to(dt)
-    color_c, sigma_c = net_out(sd, t_c, d_cam, d_wrd, c2w)
+    color_c, sigma_c = net_out(sd, t_c, d_cam, d_wrd, c2w, faithful32=faithful32, emulate_bf16=emulate_bf16)
     delta_c = torch.from_numpy(((far - near) / f32(n_coarse)).astype(f32)).to(dt)[:, None].expand(-1, n_coarse)
     w_c = get_density(delta_c, sigma_c)                                   # nerf.py:293-295
     t_f, idx, u, cdf = resample(t_c, w_c, n_fine, delta0=delta0, return_aux=True)        # nerf.py:298
-    color_f, sigma_f = net_out(sd, t_f, d_cam, d_wrd, c2w, t_requires_path=True)
+    if detach_t_fine:   # diagnostic only: the reference does NOT detach (nerf.py:255-259)
+        t_f = t_f.detach()
+    color_f, sigma_f = net_out(sd, t_f, d_cam, d_wrd, c2w, t_requires_path=True, faithful32=faithful32,
+                               emulate_bf16=emulate_bf16)
     c_fine, w_f, t_s, _, _ = merge_sort_composite(t_c, color_c, sigma_c, t_f, color_f, sigma_f, last)
     c_coarse = color_cum(w_c, color_c)
     if return_aux:
@@ -325,13 +343,13 @@ def render_rays(sd, row, col, c2w, k_inv, near, far, n_coarse: int = 64, n_fine:
 
 
 def forward(sd, row, col, poses_bound, k_inv, n_coarse: int = 64, n_fine: int = 128, return_aux: bool = False,
-            any_step_zero=None, delta0=None):
+            any_step_zero=None, delta0=None, **kw):
     """nerf.py:333-348.  poses_bound [N,17] (float64 from the loader), cast to fp32 first."""
     pb = torch.as_tensor(poses_bound).to(torch.float32)
     c2w, _, _, _, near, far = poses_extract(pb)
     return render_rays(sd, np.asarray(row), np.asarray(col), c2w.numpy(), torch.as_tensor(k_inv).numpy(),
                        near.numpy(), far.numpy(), n_coarse, n_fine, return_aux=return_aux,
-                       any_step_zero=any_step_zero, delta0=delta0)
+                       any_step_zero=any_step_zero, delta0=delta0, **kw)
 
 
 def ray_loss(c_coarse, c_fine, c_true):

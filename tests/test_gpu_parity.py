@@ -406,3 +406,110 @@ def test_bf16_ragged_sizes(ctx, dev, golden_dir):
             r16, s16, _ = ctx.mlp_forward(BF16, t, rays[:n].contiguous(), de[:n].contiguous(), flat, packed)
             assert float((r32 - r16).abs().max()) <= 1e-2
             assert float((s32 - s16).abs().max()) <= 3e-2 * max(1.0, float(s32.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------ bf16 training path
+def _param_rels(gflat, sd):
+    from nerf_tiny_b200 import _lib
+    rels = {}
+    for (o, i, wo, bo), key in zip(_lib.layer_table(), O.LAYER_KEYS):
+        for off, n, name in ((wo, o * i, ".weight"), (bo, o, ".bias")):
+            ref = sd[key + name].grad.numpy().reshape(-1)
+            rels[(key + name).replace("network.", "")] = np.linalg.norm(gflat[off:off + n] - ref) / max(1e-20, np.linalg.norm(ref))
+    return rels
+
+
+@pytest.mark.parametrize("case,tk,wcase", [("kat8", "t_fine", "init"), ("fern64", "t_coarse", "init"),
+                                           ("fern64", "t_fine", "trained64"), ("fern64", "t_fine", "x_trained")])
+def test_mlp_bf16_backward(ctx, dev, golden_dir, case, tk, wcase):
+    """Tensor-core backward vs fp64 autograd of the oracle's bf16-operand model of the forward (emulate_bf16): the
+    kernel must produce the exact gradient of the function it evaluates.  The distance to the un-rounded fp64
+    gradient (ReLU masks flip when activations move by a bf16 ulp) is printed for reference."""
+    g = load(golden_dir, case)
+    sd32 = sd_of(wcase)
+    flat = flat_of(sd32, dev)
+    packed = ctx.pack(flat, BF16)
+    rays, _, de = ctx.raygen(cu(g["row"], dev), cu(g["col"], dev), cu(g["c2w"], dev), cu(g["k_inv"], dev))
+    t = cu(g[tk], dev)
+    rgb, sigma, ws = ctx.mlp_forward(BF16, t, rays, de, flat, packed, train=True)
+    gen = torch.Generator().manual_seed(4)
+    g_rgb = torch.randn(rgb.shape, generator=gen)
+    g_sig = torch.randn(sigma.shape, generator=gen) * 0.01
+    grads, g_t = ctx.mlp_backward(BF16, t, rays, de, flat, packed, g_rgb.to(dev), g_sig.to(dev), ws)
+    gflat = grads.cpu().numpy()
+    d_cam, d_wrd = O.ray_dirs(g["row"], g["col"], g["k_inv"], g["c2w"])
+    out = {}
+    for emu in (True, False):
+        sd = {k: v.double().requires_grad_(True) for k, v in sd32.items()}
+        tt = torch.from_numpy(g[tk]).double().requires_grad_(True)
+        color, sig = O.net_out(sd, tt, d_cam.astype(np.float64), d_wrd.astype(np.float64), g["c2w"].astype(np.float64),
+                               faithful32=True, emulate_bf16=emu)
+        if emu:
+            assert float((rgb.cpu().double() - color).abs().max()) <= 2e-3        # the model describes the kernel
+        ((color * g_rgb.double()).sum() + (sig * g_sig.double()).sum()).backward()
+        rels = _param_rels(gflat, sd)
+        ref_t = tt.grad.numpy()
+        rels["g_t"] = np.linalg.norm(g_t.cpu().numpy() - ref_t) / np.linalg.norm(ref_t)
+        out[emu] = rels
+    print("BWD", case, tk, wcase, "vs bf16-model:", {k: float("%.1e" % v) for k, v in out[True].items()})
+    print("BWD", case, tk, wcase, "vs exact fp64 (inherent):", {k: float("%.1e" % v) for k, v in out[False].items()})
+    lim = 0.1 if wcase == "x_trained" else 3e-2
+    bad = {k: v for k, v in out[True].items() if v > (lim if k != "g_t" else max(lim, 0.1))}
+    assert not bad, bad
+
+
+def _full_step_grads(dev, golden_dir, case, prec, detach):
+    from nerf_tiny_b200 import nerf
+    g = load(golden_dir, case)
+    row, col = torch.from_numpy(g["row"]), torch.from_numpy(g["col"])
+    pb, kinv = torch.from_numpy(g["poses_bound"]), torch.from_numpy(g["k_inv"])
+    tgt = torch.rand(row.shape[0], 3, generator=torch.Generator().manual_seed(3))
+    m = model_of(case, dev, prec)
+    m.train()
+    m.set_detach_t_fine(detach)
+    opt = nerf.FusedAdam(m, lr=0.0)
+    loss, cc, cf = nerf.train_step(m, opt, row, col, tgt, pb, kinv)
+    return float(loss), m.network.flat_grads().cpu().numpy().copy(), (g, pb, kinv, tgt)
+
+
+def _oracle_full_grads(case, g, pb, kinv, tgt, detach, emu):
+    sd = {k: v.double().requires_grad_(True) for k, v in sd_of(case).items()}
+    cc, cf = O.forward(sd, g["row"], g["col"], pb, kinv, detach_t_fine=detach, emulate_bf16=emu, faithful32=True)
+    loss = O.ray_loss(cc, cf, tgt.double())
+    loss.backward()
+    return float(loss), sd
+
+
+@pytest.mark.parametrize("case", ["fern64", "trained64"])
+def test_full_step_gradient_fp32(dev, golden_dir, case):
+    """Whole backward chain (sort -> composite -> MLP -> resample -> composite -> MLP) vs fp64 autograd of the oracle.
+    With t_fine detached the gradient is well conditioned and must match tightly; the reference's full gradient
+    (t_fine not detached, nerf.py:255-259) is dominated by fp32 noise even in the reference itself,
+    so it is only sanity-checked."""
+    loss, gflat, (g, pb, kinv, tgt) = _full_step_grads(dev, golden_dir, case, "fp32", True)
+    ref_loss, sd = _oracle_full_grads(case, g, pb, kinv, tgt, True, False)
+    assert abs(loss - ref_loss) <= 1e-4 * ref_loss
+    rels = _param_rels(gflat, sd)
+    print("FULL fp32 detach", case, {k: float("%.1e" % v) for k, v in rels.items()})
+    # t_fine itself carries ~1e-5 absolute fp32 noise (slope = delta/(w+1e-7)); times w_l = 3217 that decorrelates the
+    # top-frequency features, which only the first layer's weight gradient sees directly
+    bad = {k: v for k, v in rels.items() if v > (0.15 if k.startswith("point_layer.0.0") else 3e-2)}
+    assert not bad, bad
+    loss, gflat, _ = _full_step_grads(dev, golden_dir, case, "fp32", False)
+    ref_loss, sd = _oracle_full_grads(case, g, pb, kinv, tgt, False, False)
+    rels = _param_rels(gflat, sd)
+    print("FULL fp32 with t-path", case, {k: float("%.1e" % v) for k, v in rels.items()})
+    assert np.isfinite(max(rels.values())) and max(rels.values()) < 3.0
+
+
+@pytest.mark.parametrize("case", ["fern64", "trained64"])
+def test_full_step_gradient_bf16(dev, golden_dir, case):
+    loss, gflat, (g, pb, kinv, tgt) = _full_step_grads(dev, golden_dir, case, "bf16", True)
+    ref_loss, sd = _oracle_full_grads(case, g, pb, kinv, tgt, True, True)
+    assert abs(loss - ref_loss) <= 2e-3 * ref_loss
+    rels = _param_rels(gflat, sd)
+    print("FULL bf16 detach vs bf16-model", case, {k: float("%.1e" % v) for k, v in rels.items()})
+    bad = {k: v for k, v in rels.items() if v > (0.25 if k.startswith("point_layer.0.0") else 6e-2)}
+    assert not bad, bad
+    loss, gflat, _ = _full_step_grads(dev, golden_dir, case, "bf16", False)
+    assert np.isfinite(gflat).all() and np.abs(gflat).max() > 0
