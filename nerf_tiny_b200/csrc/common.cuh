@@ -141,6 +141,7 @@ struct GemmTcEpi {
   int ldmask;
   const float* r1_row;  // optional rank-1 term added before the mask: v += r1_row[m] * r1_col[n]
   const float* r1_col;
+  float* colsum;        // optional fp32 [N]: += column sums of the stored matrix (fused bias gradient)
 };
 int nt_launch_gemm_tc(nt_ctx* ctx, int mn_major, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                       const GemmTcEpi& epi, cudaStream_t st);
@@ -163,3 +164,5 @@ int nt_mlp_bf16_train_forward(nt_ctx* ctx, int64_t n, int p, const float* t, con
 int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* params,
                                const float* rgb, const float* g_rgb, const float* g_sigma, float* grads, float* g_t,
                                void* ws, size_t ws_bytes, cudaStream_t st);
+int nt_launch_dw_gemm(nt_ctx* ctx, int S, const void* G, int ldg, int m_valid, const void* H, int ldh, int n_valid,
+                      float* C, int ldc, cudaStream_t st);

@@ -38,6 +38,7 @@ struct GemmTcArgs {
   int ldmask;
   const float* r1_row;  // rank-1 term v += r1_row[m] * r1_col[n] (sigma-head gradient joining point_info's)
   const float* r1_col;
+  float* colsum;        // optional [N]: += column sums of the stored matrix (bias gradient of the layer below)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -271,6 +272,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int n0 = (half * NCB + i) * 32;
         uint32_t raw[32];
         tmem_ld32(trow + n0, raw);
+        float cs[32];
+        if (g.colsum) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cs[j] = 0.f;
+        }
         if (m < g.M && n0 < g.n_valid) {
           if (g.epi == 1) {
             float* c = reinterpret_cast<float*>(g.C) + (int64_t)m * g.ldc + n0;
@@ -330,6 +336,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 if (n0 + j < g.n_valid) cf[j] = v[j];
               continue;
             }
+            if (g.colsum) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) cs[j] = v[j];
+            }
             __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(g.C) + (int64_t)m * g.ldc + n0;
             if (n0 + 32 <= g.n_valid && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
 #pragma unroll
@@ -344,9 +354,149 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
           }
         }
+        if (g.colsum && n0 < g.n_valid) {
+          // column sums over this warp's 32 rows by recursive halving: after 5 exchange steps lane L holds column L
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int j = 0; j < o; ++j) {
+              const float send = up ? cs[j] : cs[j + o];
+              const float keep = up ? cs[j + o] : cs[j];
+              cs[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          if (n0 + lane < g.n_valid) atomicAdd(g.colsum + n0 + lane, cs[0]);
+        }
       }
       tc_fence_before();
       mbar_arrive(bar(10 + as));
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight-gradient GEMM  dW[256 x N] += G^T . H  over the sample axis, both 128-row halves of the output
+// in ONE CTA so that G and H each cross HBM exactly once:  A = G stored [S][256] (MN-major, M = 256 = 4 boxes of 64),
+// B = H stored [S][N<=256].  Split-K over the samples, 3-stage TMA ring of 64-sample blocks, two TMEM accumulators
+// (columns 0-255 / 256-511), fp32 vector atomics into the flat gradient buffer.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DW_STAGES = 3;
+constexpr int DW_A_BYTES = 4 * 8192;  // 256 output rows = 4 x (64 elements x 64 samples)
+
+struct DwArgs {
+  int S;           // samples (K), multiple of 64
+  int m_valid;     // output rows actually present (<= 256)
+  int n_valid;     // output columns written
+  int kb_per_cta;  // 64-sample blocks per CTA
+  float* C;
+  int ldc;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    dw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DwArgs g) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE = DW_A_BYTES + B_BYTES;
+  constexpr int OFF_BAR = DW_STAGES * STAGE;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };  // full[3] 0-2, empty[3] 3-5, acc_full 6
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
+  const int kb_total = g.S / BK;
+  const int kb0 = blockIdx.x * g.kb_per_cta;
+  const int kb1 = min(kb_total, kb0 + g.kb_per_cta);
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023) __trap();
+    for (int s = 0; s < DW_STAGES; ++s) {
+      mbar_init(bar(s), 1);
+      mbar_init(bar(3 + s), 1);
+    }
+    mbar_init(bar(6), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++q) {
+        const uint32_t s = q % DW_STAGES;
+        mbar_wait(bar(3 + s), ((q / DW_STAGES) & 1) ^ 1);
+        mbar_expect_tx(bar(s), STAGE);
+        const uint32_t da = sbase + s * STAGE, db = da + DW_A_BYTES;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_2d(da + b * 8192, &map_a, b * 64, kb * BK, bar(s));
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b) tma_load_2d(db + b * 8192, &map_b, b * 64, kb * BK, bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(BN, true);
+      uint32_t q = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++q) {
+        const uint32_t s = q % DW_STAGES;
+        mbar_wait(bar(s), (q / DW_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = sbase + s * STAGE, b_addr = a_addr + DW_A_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t bd = desc_mnmajor(b_addr + j * 2048, 8192);
+          const uint32_t acc = (kb > kb0 || j > 0) ? 1u : 0u;
+          umma_bf16(tmem_base, desc_mnmajor(a_addr + j * 2048, 8192), bd, idesc, acc);                 // rows 0-127
+          umma_bf16(tmem_base + 256, desc_mnmajor(a_addr + 16384 + j * 2048, 8192), bd, idesc, acc);   // rows 128-255
+        }
+        umma_commit(bar(3 + s));
+      }
+      umma_commit(bar(6));
+    }
+  } else if (kb1 > kb0) {
+    const int e = warp - 2, quad = warp & 3, half = e >> 2;
+    constexpr int NCB = BN / 64;
+    mbar_wait(bar(6), 0);
+    tc_fence_after();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int m = mt * 128 + quad * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + mt * 256;
+#pragma unroll
+      for (int i = 0; i < NCB; ++i) {
+        const int n0 = (half * NCB + i) * 32;
+        uint32_t raw[32];
+        tmem_ld32(trow + n0, raw);
+        if (m < g.m_valid && n0 < g.n_valid) {
+          float* c = g.C + (int64_t)m * g.ldc + n0;
+          if (n0 + 32 <= g.n_valid && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4 * j), "f"(__uint_as_float(raw[4 * j])),
+                           "f"(__uint_as_float(raw[4 * j + 1])), "f"(__uint_as_float(raw[4 * j + 2])),
+                           "f"(__uint_as_float(raw[4 * j + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < g.n_valid) atomicAdd(c + j, __uint_as_float(raw[j]));
+          }
+        }
+      }
     }
   }
   __syncwarp();
@@ -431,6 +581,7 @@ int nt_launch_gemm_tc(nt_ctx* ctx, int mn_major, int M, int N, int K, const void
   g.epi = epi.atomic_f32 ? 1 : (epi.store_f32 ? 2 : 0);
   g.r1_row = epi.r1_row;
   g.r1_col = epi.r1_col;
+  g.colsum = epi.colsum;
   g.C = epi.C;
   g.ldc = epi.ldc;
   g.bias = epi.bias;
@@ -466,4 +617,43 @@ int nt_launch_gemm_tc(nt_ctx* ctx, int mn_major, int M, int N, int K, const void
   if (BN == 64) return launch<64, false>(ctx, ma, mb, g, st);
   if (BN == 128) return launch<128, false>(ctx, ma, mb, g, st);
   return launch<256, false>(ctx, ma, mb, g, st);
+}
+
+// dW[m_valid x n_valid] += G^T . H : G bf16 [S][ldg] (m_valid <= 256 columns used), H bf16 [S][ldh] (n_valid <= 256)
+int nt_launch_dw_gemm(nt_ctx* ctx, int S, const void* G, int ldg, int m_valid, const void* H, int ldh, int n_valid,
+                      float* C, int ldc, cudaStream_t st) {
+  if (S <= 0 || m_valid <= 0 || n_valid <= 0) return NT_OK;
+  if (S % BK != 0 || m_valid > 256 || n_valid > 256) {
+    nt_set_error("dw_gemm: S must be a multiple of 64, M,N <= 256");
+    return NT_ERR_INVALID;
+  }
+  const int BN = n_valid <= 64 ? 64 : (n_valid <= 128 ? 128 : 256);
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_map(&ma, G, S, m_valid, ldg, 64, BK)) != NT_OK) return rc;
+  if ((rc = make_map(&mb, H, S, n_valid, ldh, 64, BK)) != NT_OK) return rc;
+  DwArgs g;
+  g.S = S;
+  g.m_valid = m_valid;
+  g.n_valid = n_valid;
+  g.C = C;
+  g.ldc = ldc;
+  const int kb_total = S / BK;
+  int ctas = ctx->sm_count < kb_total ? ctx->sm_count : kb_total;
+  g.kb_per_cta = (kb_total + ctas - 1) / ctas;
+  ctas = (kb_total + g.kb_per_cta - 1) / g.kb_per_cta;
+#define DW_LAUNCH(BN_)                                                                                              \
+  {                                                                                                                 \
+    constexpr int smem = DW_STAGES * (DW_A_BYTES + BN_ * 128) + 128;                                                \
+    static bool set = false;                                                                                        \
+    if (!set) {                                                                                                     \
+      NT_CUDA(cudaFuncSetAttribute(dw_gemm_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
+      set = true;                                                                                                   \
+    }                                                                                                               \
+    dw_gemm_kernel<BN_><<<ctas, GEMM_THREADS, smem, st>>>(ma, mb, g);                                               \
+  }
+  if (BN == 64) DW_LAUNCH(64) else if (BN == 128) DW_LAUNCH(128) else DW_LAUNCH(256)
+#undef DW_LAUNCH
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
 }

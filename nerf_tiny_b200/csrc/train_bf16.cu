@@ -153,28 +153,44 @@ __global__ void heads_backward_kernel(int64_t S, const float* __restrict__ rgb, 
   }
 }
 
-// column sums of a bf16 matrix accumulated (fp32 atomics) into out[cols]
-__global__ void colsum_bf16_kernel(const bf16* __restrict__ G, int64_t rows, int cols, int ld, float* __restrict__ out,
-                                   int rows_per_block) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+// column sums of a bf16 matrix [rows][ld] accumulated (fp32 atomics) into out[cols]; cols even.
+// One thread per column PAIR (bf16x2 loads: a warp reads 128 contiguous bytes per row), 4 rows in flight per thread.
+__global__ void __launch_bounds__(128) colsum_bf16_kernel(const bf16* __restrict__ G, int64_t rows, int cols, int ld,
+                                                           float* __restrict__ out, int rows_per_block) {
+  const int cp = threadIdx.x;
+  if (2 * cp >= cols) return;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
-  float acc = 0.f;
-  for (int64_t r = r0; r < r1; ++r) acc += __bfloat162float(G[r * ld + c]);
-  atomicAdd(out + c, acc);
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(G) + cp;
+  const int64_t ldw = ld / 2;
+  int64_t r = r0;
+  for (; r + 3 < r1; r += 4) {
+    const uint32_t w0 = __ldg(base + r * ldw), w1 = __ldg(base + (r + 1) * ldw), w2 = __ldg(base + (r + 2) * ldw),
+                   w3 = __ldg(base + (r + 3) * ldw);
+    a0 += __uint_as_float(w0 << 16);
+    a1 += __uint_as_float(w0 & 0xffff0000u);
+    b0 += __uint_as_float(w1 << 16);
+    b1 += __uint_as_float(w1 & 0xffff0000u);
+    c0 += __uint_as_float(w2 << 16);
+    c1 += __uint_as_float(w2 & 0xffff0000u);
+    d0 += __uint_as_float(w3 << 16);
+    d1 += __uint_as_float(w3 & 0xffff0000u);
+  }
+  for (; r < r1; ++r) {
+    const uint32_t w0 = __ldg(base + r * ldw);
+    a0 += __uint_as_float(w0 << 16);
+    a1 += __uint_as_float(w0 & 0xffff0000u);
+  }
+  atomicAdd(out + 2 * cp, (a0 + b0) + (c0 + d0));
+  if (2 * cp + 1 < cols) atomicAdd(out + 2 * cp + 1, (a1 + b1) + (c1 + d1));
 }
 
 int colsum_bf16(nt_ctx* ctx, const bf16* G, int64_t rows, int cols, int ld, float* out, cudaStream_t st) {
-  int rpb = 512;
-  const int tx = cols >= 128 ? 128 : (cols >= 32 ? 32 : cols);
-  dim3 grid((cols + tx - 1) / tx, (unsigned)((rows + rpb - 1) / rpb));
-  if (grid.y > 65535) {
-    rpb = (int)((rows + 65534) / 65535);
-    grid.y = (unsigned)((rows + rpb - 1) / rpb);
-  }
-  colsum_bf16_kernel<<<grid, tx, 0, st>>>(G, rows, cols, ld, out, rpb);
+  const int rpb = 128;
+  const unsigned blocks = (unsigned)((rows + rpb - 1) / rpb);
+  colsum_bf16_kernel<<<blocks, 128, 0, st>>>(G, rows, cols, ld, out, rpb);
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;
 }
@@ -246,14 +262,11 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
   NT_LAUNCH_CHECK(ctx);
 
   auto dW = [&](const bf16* Gm, int ldg, int M, const bf16* Hm, int ldh, int N, float* dst, int ldc) {
-    GemmTcEpi e = epi0();
-    e.C = dst;
-    e.ldc = ldc;
-    e.atomic_f32 = 1;
-    return nt_launch_gemm_tc(ctx, 1, M, N, S, Gm, ldg, Hm, ldh, e, st);
+    return nt_launch_dw_gemm(ctx, S, Gm, ldg, M, Hm, ldh, N, dst, ldc, st);
   };
+  // dX also accumulates the column sums of what it stores = the bias gradient of the layer that produced `mask`
   auto dX = [&](const bf16* Gm, int ldg, int K, const bf16* WTm, int N, bf16* out, const bf16* mask, const float* r1_row,
-                const float* r1_col) {
+                const float* r1_col, float* db) {
     GemmTcEpi e = epi0();
     e.C = out;
     e.ldc = N;
@@ -261,6 +274,7 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
     e.ldmask = N;
     e.r1_row = r1_row;
     e.r1_col = r1_col;
+    e.colsum = db;
     return nt_launch_gemm_tc(ctx, 0, S, N, K, Gm, ldg, WTm, K, e, st);
   };
 
@@ -270,13 +284,12 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
   NT_TRY(dW(w.Gu, 128, 128, DENC, 32, 24, G + T.w[L_DIR], 280));
   NT_TRY(dW(w.Gu, 128, 128, H[8], 256, 256, G + T.w[L_DIR] + 24, 280));
   NT_TRY(colsum_bf16(ctx, w.Gu, S, 128, 128, G + T.b[L_DIR], st));
-  NT_TRY(dX(w.Gu, 128, 128, w.WT + WT_DIRINFO, 256, w.GA, nullptr, nullptr, nullptr));  // g_info (no activation)
+  NT_TRY(dX(w.Gu, 128, 128, w.WT + WT_DIRINFO, 256, w.GA, nullptr, nullptr, nullptr, G + T.b[L_INFO]));  // g_info
   // point_info (256 -> 256, linear) and the sigma head (256 -> 1, abs)
   NT_TRY(dW(w.GA, 256, 256, H[7], 256, 256, G + T.w[L_INFO], 256));
-  NT_TRY(colsum_bf16(ctx, w.GA, S, 256, 256, G + T.b[L_INFO], st));
   NT_TRY(dW(w.Gzs, 8, 1, H[7], 256, 256, G + T.w[L_SIGMA], 256));
   // g_pre7 = relu'(h7) * (g_info . W_p + g_zsig (x) w_sigma)
-  NT_TRY(dX(w.GA, 256, 256, w.WT + WT_INFO, 256, w.GB, H[7], w.gzsig, P + T.w[L_SIGMA]));
+  NT_TRY(dX(w.GA, 256, 256, w.WT + WT_INFO, 256, w.GB, H[7], w.gzsig, P + T.w[L_SIGMA], G + T.b[L_P7]));
   bf16* cur = w.GB;
   bf16* nxt = w.GA;
   for (int i = 7; i >= 1; --i) {
@@ -291,14 +304,12 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
         NT_TRY(nt_launch_gemm_tc(ctx, 0, S, 64, 256, cur, 256, w.WT + WT_ENC4, 256, e, st));
       }
     }
-    NT_TRY(colsum_bf16(ctx, cur, S, 256, 256, G + T.b[i], st));
-    NT_TRY(dX(cur, 256, 256, w.WT + WT_TRUNK + (i - 1) * 65536, 256, nxt, H[i - 1], nullptr, nullptr));
+    NT_TRY(dX(cur, 256, 256, w.WT + WT_TRUNK + (i - 1) * 65536, 256, nxt, H[i - 1], nullptr, nullptr, G + T.b[i - 1]));
     bf16* tmp = cur;
     cur = nxt;
     nxt = tmp;
   }
   NT_TRY(dW(cur, 256, 256, ENC, 64, 60, G + T.w[L_P0], 60));
-  NT_TRY(colsum_bf16(ctx, cur, S, 256, 256, G + T.b[L_P0], st));
   if (g_t) {
     GemmTcEpi e = epi0();
     e.C = w.genc;
