@@ -128,6 +128,52 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return r;
 }
 
+// fp32 atomic accumulation of 32 consecutive values: 16-byte vector reductions on the aligned middle, scalar atomics on
+// the (at most 3 + 3) unaligned head/tail elements — the flat parameter layout is only 4-byte aligned after the
+// 1-wide sigma bias
+__device__ __forceinline__ void red_add_32(float* c, const uint32_t (&raw)[32], int n_ok) {
+  const int head = (4 - (int)((reinterpret_cast<uintptr_t>(c) >> 2) & 3)) & 3;
+  if (head == 0 && n_ok >= 32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4 * j), "f"(__uint_as_float(raw[4 * j])),
+                   "f"(__uint_as_float(raw[4 * j + 1])), "f"(__uint_as_float(raw[4 * j + 2])),
+                   "f"(__uint_as_float(raw[4 * j + 3]))
+                   : "memory");
+    return;
+  }
+  // head is warp-uniform in practice (same row pitch for every lane), so these branches do not diverge
+#pragma unroll
+  for (int hh = 1; hh <= 3; ++hh) {
+    if (head == hh) {
+#pragma unroll
+      for (int j = 0; j < hh; ++j)
+        if (j < n_ok) atomicAdd(c + j, __uint_as_float(raw[j]));
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        if (hh + 4 * j + 4 <= n_ok)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + hh + 4 * j),
+                       "f"(__uint_as_float(raw[hh + 4 * j])), "f"(__uint_as_float(raw[hh + 4 * j + 1])),
+                       "f"(__uint_as_float(raw[hh + 4 * j + 2])), "f"(__uint_as_float(raw[hh + 4 * j + 3]))
+                       : "memory");
+        else {
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2)
+            if (hh + 4 * j + k2 < n_ok) atomicAdd(c + hh + 4 * j + k2, __uint_as_float(raw[hh + 4 * j + k2]));
+        }
+      }
+#pragma unroll
+      for (int j = hh + 28; j < 32; ++j)
+        if (j < n_ok) atomicAdd(c + j, __uint_as_float(raw[j]));
+    }
+  }
+  if (head == 0) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_ok) atomicAdd(c + j, __uint_as_float(raw[j]));
+  }
+}
+
 template <int BN, bool MN_MAJOR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmTcArgs g) {
@@ -263,9 +309,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       const int mt = item % m_tiles;
       const uint32_t as = it & 1;
+      const int m = mt * BM + row_in_tile;
+      // ReLU' masks of this thread's row come from HBM: fetch them while the MMAs of this tile are still running
+      uint4 mpre[NCB][4];
+      const bool mask_fast = g.mask != nullptr && g.epi == 0 && m < g.M && (half + 1) * NCB * 32 <= g.n_valid &&
+                             ((reinterpret_cast<uintptr_t>(g.mask + (int64_t)m * g.ldmask) & 15) == 0);
+      if (mask_fast) {
+        const uint4* mk = reinterpret_cast<const uint4*>(g.mask + (int64_t)m * g.ldmask + half * NCB * 32);
+#pragma unroll
+        for (int i = 0; i < NCB; ++i)
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) mpre[i][qd] = __ldg(mk + i * 4 + qd);
+      }
       mbar_wait(bar(8 + as), (it >> 1) & 1);
       tc_fence_after();
-      const int m = mt * BM + row_in_tile;
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
 #pragma unroll
       for (int i = 0; i < NCB; ++i) {
@@ -280,18 +337,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (m < g.M && n0 < g.n_valid) {
           if (g.epi == 1) {
             float* c = reinterpret_cast<float*>(g.C) + (int64_t)m * g.ldc + n0;
-            if (n0 + 32 <= g.n_valid && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4 * j), "f"(__uint_as_float(raw[4 * j])),
-                             "f"(__uint_as_float(raw[4 * j + 1])), "f"(__uint_as_float(raw[4 * j + 2])),
-                             "f"(__uint_as_float(raw[4 * j + 3]))
-                             : "memory");
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < g.n_valid) atomicAdd(c + j, __uint_as_float(raw[j]));
-            }
+            red_add_32(c, raw, g.n_valid - n0);
           } else {
             float v[32];
 #pragma unroll
@@ -318,7 +364,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               const uint4* mk = reinterpret_cast<const uint4*>(g.mask + (int64_t)m * g.ldmask + n0);
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) {
-                const uint4 mm = __ldg(mk + qd);
+                const uint4 mm = mask_fast ? mpre[i][qd] : __ldg(mk + qd);
                 const uint32_t w[4] = {mm.x, mm.y, mm.z, mm.w};
 #pragma unroll
                 for (int k2 = 0; k2 < 4; ++k2) {
@@ -483,18 +529,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tmem_ld32(trow + n0, raw);
         if (m < g.m_valid && n0 < g.n_valid) {
           float* c = g.C + (int64_t)m * g.ldc + n0;
-          if (n0 + 32 <= g.n_valid && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + 4 * j), "f"(__uint_as_float(raw[4 * j])),
-                           "f"(__uint_as_float(raw[4 * j + 1])), "f"(__uint_as_float(raw[4 * j + 2])),
-                           "f"(__uint_as_float(raw[4 * j + 3]))
-                           : "memory");
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < g.n_valid) atomicAdd(c + j, __uint_as_float(raw[j]));
-          }
+          red_add_32(c, raw, g.n_valid - n0);
         }
       }
     }
