@@ -157,6 +157,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on STDOUT when NCCL_DEBUG>=VERSION; the contract is one JSON line there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     from nerf_tiny_b200 import nerf, ops, _lib, build
     build.build()

@@ -52,9 +52,12 @@ def main():
     torch.set_num_threads(8)
     ref = RH.import_reference()
     z = np.load(os.path.join(GOLD, "trained_weights_fp16.npz"))
-    samples = [float(z["__psnr"][-50:].mean())]          # trial 0 = the unperturbed run already in the fixture
     path = os.path.join(GOLD, "train_spread.npz")
-    for trial in range(1, n_runs + 1):
+    if os.path.exists(path):                              # resume: keep the samples already measured
+        samples = [float(x) for x in np.load(path)["ref_psnr_last50"]]
+    else:
+        samples = [float(z["__psnr"][-50:].mean())]      # trial 0 = the unperturbed run already in the fixture
+    for trial in range(len(samples), n_runs + 1):
         samples.append(run(ref, trial))
         print("[spread] reference PSNR(last 50) samples:", ["%.3f" % s for s in samples], flush=True)
         np.savez(path, ref_psnr_last50=np.array(samples), perturbation=1e-6, steps=250, n_rays=256, lr=1e-3, seed=123)
