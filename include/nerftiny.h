@@ -64,8 +64,11 @@ int nt_layer_table(nt_layer_desc out[NT_N_LAYERS]);
 /* Options.  NT_OPT_DETACH_T_FINE (diagnostic, default 0): nt_render_backward treats t_fine as a constant, i.e. drops
  * the gradient path t_fine -> cdf/weights -> coarse sigma that the reference keeps (nerf.py:255-259).  The fp32
  * gradient along that path is ill-conditioned; the switch lets tests compare the well-conditioned
- * part of the gradient tightly. */
+ * part of the gradient tightly.
+ * NT_OPT_MLP_TC_VERSION (default 0 = 5): schedule of the fused bf16 encode+MLP kernel — 5 tile pair in lock-step,
+ * 6 staggered tiles + 2-CTA cluster weight multicast, 7 staggered tiles + tcgen05 cta_group::2. */
 #define NT_OPT_DETACH_T_FINE 1
+#define NT_OPT_MLP_TC_VERSION 2
 int nt_set_option(nt_ctx* ctx, int key, int value);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t nt_launch_count(const nt_ctx* ctx);

@@ -57,6 +57,7 @@ extern "C" int nt_create(nt_ctx** out, int device, int n_coarse, int n_fine) {
   c->sm_count = prop.multiProcessorCount;
   c->launches = 0;
   c->opt_detach_t_fine = 0;
+  c->opt_tc_version = 0;
   c->d_flags = nullptr;
   if (cudaMalloc(&c->d_flags, 4 * sizeof(int)) != cudaSuccess || cudaMemset(c->d_flags, 0, 4 * sizeof(int)) != cudaSuccess) {
     nt_set_error("cudaMalloc of the status flags failed");
@@ -79,6 +80,11 @@ extern "C" int nt_set_option(nt_ctx* ctx, int key, int value) {
   NT_REQUIRE(ctx, "null ctx");
   if (key == NT_OPT_DETACH_T_FINE) {
     ctx->opt_detach_t_fine = value != 0;
+    return NT_OK;
+  }
+  if (key == NT_OPT_MLP_TC_VERSION) {
+    NT_REQUIRE(value == 0 || (value >= 5 && value <= 7), "mlp_tc version must be 0 (default), 5, 6 or 7");
+    ctx->opt_tc_version = value;
     return NT_OK;
   }
   nt_set_error("unknown option %d", key);

@@ -18,6 +18,7 @@ struct nt_ctx {
   int* d_flags;  // [0] = any_step_zero scratch, [1] = resample range status
   int64_t launches;
   int opt_detach_t_fine;
+  int opt_tc_version;
 };
 
 void nt_set_error(const char* fmt, ...);

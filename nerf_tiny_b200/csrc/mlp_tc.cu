@@ -14,6 +14,7 @@
 //     sigmoid) are evaluated on CUDA cores from the fp32 accumulators in the same pass.
 // Skip (nerf.py:109) and view (nerf.py:118) concatenations are extra K-chunks accumulated into the same TMEM tile.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -562,6 +563,822 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
   }
 }
 
+// =========================================================================================================
+// v6: tile-STAGGERED schedule on a 2-CTA cluster.
+// The tensor core alternates between the CTA's two tiles one whole layer at a time: MMA(A,L), MMA(B,L), MMA(A,L+1) ...
+// so the epilogue of tile A (all 16 epilogue warps, one column quarter each) runs while tile B multiplies and vice
+// versa.  Each tile therefore makes its own pass over the layer's weight chunks; to keep the L2->SM weight stream at
+// one chunk per 256 samples, the two CTAs of a cluster share one ring: each CTA fetches HALF of every chunk and
+// TMA-multicasts it into both CTAs' shared memory.  A ring slot is released when BOTH CTAs' MMAs have retired
+// (tcgen05.commit multicast onto both CTAs' empty barriers).
+// =========================================================================================================
+namespace v6 {
+
+constexpr int OFF_BIAS = OFF_BAR + 128;               // 2 x 1 KB double-buffered bias rows (layer parity)
+constexpr int SMEM6_BYTES = OFF_BIAS + 2048;
+enum { B_W_FULL = 0, B_W_EMPTY = 2, B_ACC_FULL = 4, B_ACT_READY = 6, B_BIAS_FULL = 8 };
+constexpr int EPI_THREADS = 512;
+constexpr int BAR_ID_EPI_ALL = 5;                     // named barrier over all epilogue threads (ids 1-4: row quads)
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tma_bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
+// epilogue of one tile-layer for one thread: row `row` of the tile, column quarter `quarter`
+template <int KIND, bool STASH>
+__device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter, uint32_t tmem_row, uint32_t act,
+                                           uint32_t bias_s, const float* __restrict__ aux_g, int quad_bar, const RowSwz sw,
+                                           int64_t s, bool valid) {
+  constexpr int NCB = KIND == EPI_COLOUR ? 1 : 2;  // 32-column blocks per quarter
+  const int cb0 = quarter * NCB;
+  __nv_bfloat16* stp = STASH ? P.st[L] + s * (KIND == EPI_COLOUR ? 128 : 256) : nullptr;
+  float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  uint32_t buf[2][32];
+  tmem_ld32_issue(tmem_row + cb0 * 32, buf[0]);
+#pragma unroll
+  for (int i = 0; i < NCB; ++i) {
+    const int cb = cb0 + i;
+    uint32_t(&raw)[32] = buf[i & 1];
+    tmem_ld_wait(raw);
+    if (i + 1 < NCB) tmem_ld32_issue(tmem_row + (cb + 1) * 32, buf[(i + 1) & 1]);
+    float4 b4[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b4[j] = lds128(bias_s + cb * 128 + j * 16);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b4[j].x;
+      v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4[j].y;
+      v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4[j].z;
+      v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4[j].w;
+    }
+    if (KIND == EPI_RELU_SIGMA) {  // sigma head (nerf.py:94, :114); weights from the fp32 side block in L1/L2
+      const float4* __restrict__ ws = reinterpret_cast<const float4*>(aux_g + 7 * AUX_REC_FLOATS + AUX_EXTRA + cb * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w4 = __ldg(ws + j);
+        sig_acc = fmaf(fmaxf(v[4 * j + 0], 0.f), w4.x, sig_acc);
+        sig_acc = fmaf(fmaxf(v[4 * j + 1], 0.f), w4.y, sig_acc);
+        sig_acc = fmaf(fmaxf(v[4 * j + 2], 0.f), w4.z, sig_acc);
+        sig_acc = fmaf(fmaxf(v[4 * j + 3], 0.f), w4.w, sig_acc);
+      }
+    }
+    if (KIND == EPI_COLOUR) {  // colour head (nerf.py:99, :119) on u = relu(.)
+      const float4* __restrict__ wc = reinterpret_cast<const float4*>(aux_g + 9 * AUX_REC_FLOATS + AUX_EXTRA + cb * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w0 = __ldg(wc + j), w1 = __ldg(wc + 32 + j), w2 = __ldg(wc + 64 + j);
+        const float u0 = fmaxf(v[4 * j], 0.f), u1 = fmaxf(v[4 * j + 1], 0.f), u2 = fmaxf(v[4 * j + 2], 0.f),
+                    u3 = fmaxf(v[4 * j + 3], 0.f);
+        c0 = fmaf(u0, w0.x, fmaf(u1, w0.y, fmaf(u2, w0.z, fmaf(u3, w0.w, c0))));
+        c1 = fmaf(u0, w1.x, fmaf(u1, w1.y, fmaf(u2, w1.z, fmaf(u3, w1.w, c1))));
+        c2 = fmaf(u0, w2.x, fmaf(u1, w2.y, fmaf(u2, w2.z, fmaf(u3, w2.w, c2))));
+      }
+      if (STASH && valid) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) =
+              make_uint4(pack_bf16_relu(v[8 * qd], v[8 * qd + 1]), pack_bf16_relu(v[8 * qd + 2], v[8 * qd + 3]),
+                         pack_bf16_relu(v[8 * qd + 4], v[8 * qd + 5]), pack_bf16_relu(v[8 * qd + 6], v[8 * qd + 7]));
+      }
+    } else {  // next layer's A operand: K-chunk cb/2 (= this thread's quarter), 16-byte chunks (cb%2)*4 .. +3
+      const uint32_t dst = act + (cb >> 1) * CHUNK_A_BYTES;
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          w[e] = KIND == EPI_LINEAR ? pack_bf16(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1])
+                                    : pack_bf16_relu(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1]);
+        st_shared_v4(sw.addr(dst, (cb & 1) * 4 + qd), w[0], w[1], w[2], w[3]);
+        if (STASH && valid) *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  // heads: the 4 column quarters of a row live in warps q, q+4, q+8, q+12 (same TMEM lanes): quarters 1-3 park their
+  // partial sums in accumulator columns they have already drained, quarter 0 adds them up after a 128-thread barrier
+  if (KIND == EPI_RELU_SIGMA || KIND == EPI_COLOUR) {
+    constexpr int QW = KIND == EPI_COLOUR ? 32 : 64;  // columns per quarter
+    if (quarter != 0) tmem_st4(tmem_row + quarter * QW, sig_acc, c0, c1, c2);
+    tc_fence_before();
+    asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+    tc_fence_after();
+    if (quarter == 0) {
+#pragma unroll
+      for (int q = 1; q < 4; ++q) {
+        float o_s, o0, o1, o2;
+        tmem_ld4(tmem_row + q * QW, o_s, o0, o1, o2);
+        sig_acc += o_s;
+        c0 += o0;
+        c1 += o1;
+        c2 += o2;
+      }
+      if (KIND == EPI_RELU_SIGMA) {
+        const float z = sig_acc + __ldg(aux_g + 7 * AUX_REC_FLOATS + AUX_SIG_B);
+        if (valid) P.sigma[s] = fabsf(z);
+        if (STASH && valid) P.st_zsig[s] = z;
+      } else if (valid) {
+        const float* cbias = aux_g + 9 * AUX_REC_FLOATS + AUX_COL_B;
+        P.rgb[s * 3 + 0] = 1.f / (1.f + __expf(-(c0 + __ldg(cbias))));
+        P.rgb[s * 3 + 1] = 1.f / (1.f + __expf(-(c1 + __ldg(cbias + 1))));
+        P.rgb[s * 3 + 2] = 1.f / (1.f + __expf(-(c2 + __ldg(cbias + 2))));
+      }
+    }
+  }
+}
+
+template <bool STASH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc6_kernel(const TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_rank();
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 96);
+  const uint8_t* aux_bytes_g = P.packed + PACKED_W_BYTES;
+  const int iters = (P.num_pairs + (int)gridDim.x - 1) / (int)gridDim.x;  // same trip count in both CTAs of a cluster
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023) __trap();
+    for (int s = 0; s < N_STAGES; ++s) {
+      mbar_init(bar(B_W_FULL + s), 1);
+      mbar_init(bar(B_W_EMPTY + s), 2);  // one tcgen05.commit from each CTA of the cluster
+    }
+    for (int tl = 0; tl < 2; ++tl) {
+      mbar_init(bar(B_ACC_FULL + tl), 1);
+      mbar_init(bar(B_ACT_READY + tl), EPI_THREADS);
+      mbar_init(bar(B_BIAS_FULL + tl), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == WARP_MMA) tmem_alloc_512(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == WARP_TMA) {
+    // ===================== TMA producer: my half of every chunk, multicast to both CTAs =====================
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int itp = 0; itp < iters; ++itp) {
+        const uint8_t* src = P.packed;
+        for (int L = 0; L < N_MMA_LAYERS; ++L) {
+          const uint32_t bytes = chunk_bytes(L), hbytes = bytes / 2;
+          for (int tl = 0; tl < 2; ++tl) {
+            for (int kc = 0; kc < layer_chunks(L); ++kc, ++q) {
+              const uint32_t stage = q & 1;
+              mbar_wait(bar(B_W_EMPTY + stage), ((q >> 1) & 1) ^ 1);
+              mbar_expect_tx(bar(B_W_FULL + stage), bytes);
+              tma_bulk_g2s_mc(sbase + OFF_W + stage * W_STAGE_BYTES + crank * hbytes, src + kc * bytes + crank * hbytes,
+                              hbytes, bar(B_W_FULL + stage), (uint16_t)3);
+            }
+          }
+          src += layer_chunks(L) * bytes;
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ===================== MMA issuer: whole layer of tile A, then whole layer of tile B =====================
+    if (lane == 0) {
+      uint32_t q = 0, lit = 0;
+      for (int itp = 0; itp < iters; ++itp) {
+        for (int L = 0; L < N_MMA_LAYERS; ++L, ++lit) {
+          const int nch = layer_chunks(L);
+          const uint32_t idesc = umma_idesc(layer_n(L));
+          for (int tl = 0; tl < 2; ++tl) {
+            mbar_wait(bar(B_ACT_READY + tl), lit & 1);  // operand written + accumulator drained
+            tc_fence_after();
+            if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4)
+              reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + tl * 2] = clock64();
+            const uint32_t d_tmem = tmem_base + tl * 256;
+            for (int kc = 0; kc < nch; ++kc, ++q) {
+              const uint32_t stage = q & 1;
+              mbar_wait(bar(B_W_FULL + stage), (q >> 1) & 1);
+              tc_fence_after();
+              const uint32_t b_addr = sbase + OFF_W + stage * W_STAGE_BYTES;
+              const bool from_enc = (L == 0) || (kc == 4);
+              const uint32_t a_addr = from_enc ? sbase + OFF_ENC + tl * CHUNK_A_BYTES
+                                               : sbase + OFF_ACT + tl * ACT_BYTES + kc * CHUNK_A_BYTES;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_bf16(d_tmem, umma_desc(a_addr + j * 32), umma_desc(b_addr + j * 32), idesc, (kc | j) != 0);
+              umma_commit_mc(bar(B_W_EMPTY + stage), (uint16_t)3);  // slot free in BOTH CTAs once these MMAs retire
+            }
+            umma_commit(bar(B_ACC_FULL + tl));
+            if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4)
+              reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + tl * 2 + 1] = clock64();
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== 16 encode + epilogue warps, serving tile A and tile B alternately ==================
+    const int quad = warp & 3, quarter = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int quad_bar = 1 + quad;
+    const float* __restrict__ aux_g = reinterpret_cast<const float*>(aux_bytes_g);
+    RowSwz sw;
+    sw.row_off = row * 128;
+    sw.x4 = (row & 7) << 4;
+    const uint32_t tmem_q = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t it = 0;        // per-tile layer counter (acc_full / act_ready parity)
+    uint32_t bias_use[2] = {0, 0};
+    const bool loader = threadIdx.x == 0;
+    if (loader) {  // biases of layers 0 and 1 (1 KB each) into the two buffers
+      for (int b = 0; b < 2; ++b) {
+        mbar_expect_tx(bar(B_BIAS_FULL + b), 1024);
+        tma_bulk_g2s(sbase + OFF_BIAS + b * 1024, aux_bytes_g + b * (AUX_REC_FLOATS * 4), 1024, bar(B_BIAS_FULL + b));
+      }
+    }
+    for (int itp = 0; itp < iters; ++itp) {
+      const int pair = blockIdx.x + itp * (int)gridDim.x;
+      int64_t s_t[2];
+      bool valid_t[2];
+      int64_t ray_t[2];
+      // ---- positional encoding of both tiles' samples: this thread = one row, feature pairs 8*quarter .. +7 ----
+#pragma unroll
+      for (int tl = 0; tl < 2; ++tl) {
+        const int64_t s = ((int64_t)pair * 2 + tl) * TILE_M + row;
+        const bool valid = pair < P.num_pairs && s < P.total;
+        const int64_t sc = valid ? s : P.total - 1;
+        const int64_t ray = sc / P.p;
+        s_t[tl] = s;
+        valid_t[tl] = valid;
+        ray_t[tl] = ray;
+        const float4* rp = reinterpret_cast<const float4*>(P.rays + ray * 16);
+        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+        const float tt = __ldg(P.t + sc);
+        const float pc0 = __fmul_rn(r0.x, tt), pc1 = __fmul_rn(r0.y, tt), pc2 = __fmul_rn(r0.z, tt);
+        float pos[3];
+        pos[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.w, pc0), __fmul_rn(r1.x, pc1)), __fmul_rn(r1.y, pc2)), r3.x);
+        pos[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.z, pc0), __fmul_rn(r1.w, pc1)), __fmul_rn(r2.x, pc2)), r3.y);
+        pos[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.y, pc0), __fmul_rn(r2.z, pc1)), __fmul_rn(r2.w, pc2)), r3.z);
+        uint32_t f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pi = quarter * 8 + i;  // feature pair index = c*10 + l
+          if (pi < 30) {
+            const int c = pi / 10, l = pi % 10;
+            const float x = c == 0 ? pos[0] : (c == 1 ? pos[1] : pos[2]);
+            float sn, cs;
+            fast_sincos(__fmul_rn(__uint_as_float(c_tc_freq_point[l]), x), sn, cs);
+            f[i] = pack_bf16(sn, cs);
+          } else {
+            f[i] = 0u;  // K padded 60 -> 64
+          }
+        }
+        const uint32_t enc = sbase + OFF_ENC + tl * CHUNK_A_BYTES;
+        st_shared_v4(sw.addr(enc, quarter * 2), f[0], f[1], f[2], f[3]);
+        st_shared_v4(sw.addr(enc, quarter * 2 + 1), f[4], f[5], f[6], f[7]);
+        if (STASH && valid) {
+          uint4* d = reinterpret_cast<uint4*>(P.st_enc + s * 64 + quarter * 16);
+          d[0] = make_uint4(f[0], f[1], f[2], f[3]);
+          d[1] = make_uint4(f[4], f[5], f[6], f[7]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar(B_ACT_READY + tl));
+      }
+
+      for (int L = 0; L < N_MMA_LAYERS; ++L, ++it) {
+        const int bb = L & 1;
+        const uint32_t bias_s = sbase + OFF_BIAS + bb * 1024;
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl) {
+          const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
+          const uint32_t enc = sbase + OFF_ENC + tl * CHUNK_A_BYTES;
+          const uint32_t tmem_row = tmem_q + tl * 256;
+          mbar_wait(bar(B_ACC_FULL + tl), it & 1);
+          tc_fence_after();
+          if (tl == 0) mbar_wait(bar(B_BIAS_FULL + bb), bias_use[bb] & 1);
+          if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
+            reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 4 + tl * 2] = clock64();
+          if (L == 7)
+            epilogue_q<EPI_RELU_SIGMA, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+          else if (L == 8)
+            epilogue_q<EPI_LINEAR, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+          else if (L == 9)
+            epilogue_q<EPI_COLOUR, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+          else
+            epilogue_q<EPI_RELU, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+          if (L == 4) {
+            // the xyz features of this tile are dead (all its MMAs retired): store the view features in their place
+            if (quarter == 0) {
+              const float4* de = reinterpret_cast<const float4*>(P.dir_enc + ray_t[tl] * 24);
+              uint32_t f[12];
+#pragma unroll
+              for (int j = 0; j < 6; ++j) {
+                const float4 d4 = __ldg(de + j);
+                f[2 * j] = pack_bf16(d4.x, d4.y);
+                f[2 * j + 1] = pack_bf16(d4.z, d4.w);
+              }
+#pragma unroll
+              for (int j = 0; j < 3; ++j) st_shared_v4(sw.addr(enc, j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              st_shared_v4(sw.addr(enc, 3), 0u, 0u, 0u, 0u);
+              if (STASH && valid_t[tl]) {
+                uint4* d = reinterpret_cast<uint4*>(P.st_denc + s_t[tl] * 32);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) d[j] = make_uint4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                d[3] = make_uint4(0u, 0u, 0u, 0u);
+              }
+            } else if (quarter == 1) {
+#pragma unroll
+              for (int j = 4; j < 8; ++j) st_shared_v4(sw.addr(enc, j), 0u, 0u, 0u, 0u);
+            }
+          }
+          if (L != 9) {
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar(B_ACT_READY + tl));
+          }
+          if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
+            reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 5 + tl * 2] = clock64();
+        }
+        // both tiles are done with this layer's bias row: refill the buffer with layer L+2's (next pair's for L = 8, 9)
+        ++bias_use[bb];
+        asm volatile("bar.sync %0, %1;" ::"r"(BAR_ID_EPI_ALL), "r"(EPI_THREADS) : "memory");
+        if (loader) {
+          const int Ln = (L + 2) % N_MMA_LAYERS;
+          const bool more = (L + 2 < N_MMA_LAYERS) || (itp + 1 < iters);
+          if (more) {
+            fence_proxy_async();
+            mbar_expect_tx(bar(B_BIAS_FULL + bb), 1024);
+            tma_bulk_g2s(sbase + OFF_BIAS + bb * 1024, aux_bytes_g + Ln * (AUX_REC_FLOATS * 4), 1024, bar(B_BIAS_FULL + bb));
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc_512(tmem_base);
+  }
+}
+
+}  // namespace v6
+
+// =========================================================================================================
+// v7: tile-STAGGERED schedule with CTA-PAIR MMAs (tcgen05 cta_group::2).
+// As v6 the tensor cores alternate between the two tiles one whole layer at a time so that one tile's epilogue hides
+// behind the other tile's MMAs, and each tile makes its own pass over the layer's weight chunks.  v6 showed that a
+// single SM cannot ingest a full 32 KB chunk per 512 MMA-cycles; here the two CTAs of a cluster form one 256-row MMA
+// (M = 2 x 128 rows, one tile from each CTA) whose B operand is SPLIT across the pair: each CTA streams only its
+// N-half of every chunk (16 KB, 4-stage ring).  The leader CTA's elected thread issues tcgen05.mma.cta_group::2; the
+// peer CTA's otherwise idle MMA warp relays "operand ready" / "weights landed" to the leader with remote mbarrier
+// arrives; completion (tcgen05.commit.cta_group::2 multicast) wakes the epilogue warps and producers of both CTAs.
+// =========================================================================================================
+namespace v7 {
+
+constexpr int NST = 4;                                // ring stages of 16 KB (this CTA's N-half of a chunk)
+__host__ __device__ constexpr bool stationary(int L) { return layer_chunks(L) <= NST; }
+constexpr int HALF_STAGE = W_STAGE_BYTES / 2;
+constexpr int OFF_BIAS = OFF_BAR + 256;               // 2 x 1 KB double-buffered bias rows (layer parity)
+constexpr int SMEM7_BYTES = OFF_BIAS + 2048;
+enum { B_W_FULL = 0, B_W_EMPTY = 4, B_ACC_FULL = 8, B_ACT_READY = 10, B_BIAS_FULL = 12, B_PEER_ACT = 14, B_PEER_W = 16 };
+constexpr int EPI_THREADS = 512;
+constexpr int BAR_ID_EPI_ALL = 5;                     // named barrier over all epilogue threads (ids 1-4: row quads)
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// M = 256 (both CTAs' 128 rows), D = f32, A = B = bf16, K-major
+__host__ __device__ constexpr uint32_t umma2_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+__device__ __forceinline__ void remote_arrive(uint32_t local_bar, uint32_t target_cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_bar), "r"(target_cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins == 1024) t0 = clock64();
+    if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tmem2_alloc_512(uint32_t smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_slot) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem2_dealloc_512(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+
+// epilogue of one tile-layer for one thread: row `row` of the tile, column quarter `quarter`
+template <int KIND, bool STASH>
+__device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter, uint32_t tmem_row, uint32_t act,
+                                           uint32_t bias_s, const float* __restrict__ aux_g, int quad_bar, const RowSwz sw,
+                                           int64_t s, bool valid) {
+  constexpr int NCB = KIND == EPI_COLOUR ? 1 : 2;  // 32-column blocks per quarter
+  const int cb0 = quarter * NCB;
+  __nv_bfloat16* stp = STASH ? P.st[L] + s * (KIND == EPI_COLOUR ? 128 : 256) : nullptr;
+  float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  uint32_t buf[2][32];
+  tmem_ld32_issue(tmem_row + cb0 * 32, buf[0]);
+#pragma unroll
+  for (int i = 0; i < NCB; ++i) {
+    const int cb = cb0 + i;
+    uint32_t(&raw)[32] = buf[i & 1];
+    tmem_ld_wait(raw);
+    if (i + 1 < NCB) tmem_ld32_issue(tmem_row + (cb + 1) * 32, buf[(i + 1) & 1]);
+    float4 b4[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b4[j] = lds128(bias_s + cb * 128 + j * 16);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b4[j].x;
+      v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4[j].y;
+      v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4[j].z;
+      v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4[j].w;
+    }
+    if (KIND == EPI_RELU_SIGMA) {  // sigma head (nerf.py:94, :114); weights from the fp32 side block in L1/L2
+      const float4* __restrict__ ws = reinterpret_cast<const float4*>(aux_g + 7 * AUX_REC_FLOATS + AUX_EXTRA + cb * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w4 = __ldg(ws + j);
+        sig_acc = fmaf(fmaxf(v[4 * j + 0], 0.f), w4.x, sig_acc);
+        sig_acc = fmaf(fmaxf(v[4 * j + 1], 0.f), w4.y, sig_acc);
+        sig_acc = fmaf(fmaxf(v[4 * j + 2], 0.f), w4.z, sig_acc);
+        sig_acc = fmaf(fmaxf(v[4 * j + 3], 0.f), w4.w, sig_acc);
+      }
+    }
+    if (KIND == EPI_COLOUR) {  // colour head (nerf.py:99, :119) on u = relu(.)
+      const float4* __restrict__ wc = reinterpret_cast<const float4*>(aux_g + 9 * AUX_REC_FLOATS + AUX_EXTRA + cb * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w0 = __ldg(wc + j), w1 = __ldg(wc + 32 + j), w2 = __ldg(wc + 64 + j);
+        const float u0 = fmaxf(v[4 * j], 0.f), u1 = fmaxf(v[4 * j + 1], 0.f), u2 = fmaxf(v[4 * j + 2], 0.f),
+                    u3 = fmaxf(v[4 * j + 3], 0.f);
+        c0 = fmaf(u0, w0.x, fmaf(u1, w0.y, fmaf(u2, w0.z, fmaf(u3, w0.w, c0))));
+        c1 = fmaf(u0, w1.x, fmaf(u1, w1.y, fmaf(u2, w1.z, fmaf(u3, w1.w, c1))));
+        c2 = fmaf(u0, w2.x, fmaf(u1, w2.y, fmaf(u2, w2.z, fmaf(u3, w2.w, c2))));
+      }
+      if (STASH && valid) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) =
+              make_uint4(pack_bf16_relu(v[8 * qd], v[8 * qd + 1]), pack_bf16_relu(v[8 * qd + 2], v[8 * qd + 3]),
+                         pack_bf16_relu(v[8 * qd + 4], v[8 * qd + 5]), pack_bf16_relu(v[8 * qd + 6], v[8 * qd + 7]));
+      }
+    } else {  // next layer's A operand: K-chunk cb/2 (= this thread's quarter), 16-byte chunks (cb%2)*4 .. +3
+      const uint32_t dst = act + (cb >> 1) * CHUNK_A_BYTES;
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          w[e] = KIND == EPI_LINEAR ? pack_bf16(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1])
+                                    : pack_bf16_relu(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1]);
+        st_shared_v4(sw.addr(dst, (cb & 1) * 4 + qd), w[0], w[1], w[2], w[3]);
+        if (STASH && valid) *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  // heads: the 4 column quarters of a row live in warps q, q+4, q+8, q+12 (same TMEM lanes): quarters 1-3 park their
+  // partial sums in accumulator columns they have already drained, quarter 0 adds them up after a 128-thread barrier
+  if (KIND == EPI_RELU_SIGMA || KIND == EPI_COLOUR) {
+    constexpr int QW = KIND == EPI_COLOUR ? 32 : 64;  // columns per quarter
+    if (quarter != 0) tmem_st4(tmem_row + quarter * QW, sig_acc, c0, c1, c2);
+    tc_fence_before();
+    asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+    tc_fence_after();
+    if (quarter == 0) {
+#pragma unroll
+      for (int q = 1; q < 4; ++q) {
+        float o_s, o0, o1, o2;
+        tmem_ld4(tmem_row + q * QW, o_s, o0, o1, o2);
+        sig_acc += o_s;
+        c0 += o0;
+        c1 += o1;
+        c2 += o2;
+      }
+      if (KIND == EPI_RELU_SIGMA) {
+        const float z = sig_acc + __ldg(aux_g + 7 * AUX_REC_FLOATS + AUX_SIG_B);
+        if (valid) P.sigma[s] = fabsf(z);
+        if (STASH && valid) P.st_zsig[s] = z;
+      } else if (valid) {
+        const float* cbias = aux_g + 9 * AUX_REC_FLOATS + AUX_COL_B;
+        P.rgb[s * 3 + 0] = 1.f / (1.f + __expf(-(c0 + __ldg(cbias))));
+        P.rgb[s * 3 + 1] = 1.f / (1.f + __expf(-(c1 + __ldg(cbias + 1))));
+        P.rgb[s * 3 + 2] = 1.f / (1.f + __expf(-(c2 + __ldg(cbias + 2))));
+      }
+    }
+  }
+}
+
+template <bool STASH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc7_kernel(const TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_rank();
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 200);
+  const uint8_t* aux_bytes_g = P.packed + PACKED_W_BYTES;
+  const int iters = (P.num_pairs + (int)gridDim.x - 1) / (int)gridDim.x;  // same trip count in both CTAs of a cluster
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023) __trap();
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(bar(B_W_FULL + s), 1);
+      mbar_init(bar(B_W_EMPTY + s), 1);  // the leader's tcgen05.commit.cta_group::2, multicast to both CTAs
+      mbar_init(bar(B_PEER_W + s), 1);   // (leader only) the peer's N-half of the chunk has landed
+    }
+    for (int tl = 0; tl < 2; ++tl) {
+      mbar_init(bar(B_ACC_FULL + tl), 1);
+      mbar_init(bar(B_ACT_READY + tl), EPI_THREADS);
+      mbar_init(bar(B_BIAS_FULL + tl), 1);
+      mbar_init(bar(B_PEER_ACT + tl), 1);  // (leader only) the peer's tile operand is ready
+    }
+    fence_mbar_init();
+  }
+  if (warp == WARP_MMA) tmem2_alloc_512(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == WARP_TMA) {
+    // ===================== TMA producer: my half of every chunk, multicast to both CTAs =====================
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int itp = 0; itp < iters; ++itp) {
+        const uint8_t* src = P.packed;
+        for (int L = 0; L < N_MMA_LAYERS; ++L) {
+          const uint32_t bytes = chunk_bytes(L), hbytes = bytes / 2;
+          // 4-chunk layers: the N-half of the whole layer fits the ring -> loaded ONCE, used by tile A then tile B;
+          // the 5-chunk layers (skip / view concatenation) are streamed once per tile
+          const int passes = stationary(L) ? 1 : 2;
+          for (int tl = 0; tl < passes; ++tl) {
+            for (int kc = 0; kc < layer_chunks(L); ++kc, ++q) {
+              const uint32_t stage = q % NST;
+              mbar_wait(bar(B_W_EMPTY + stage), ((q / NST) & 1) ^ 1);
+              mbar_expect_tx(bar(B_W_FULL + stage), hbytes);
+              tma_bulk_g2s(sbase + OFF_W + stage * HALF_STAGE, src + kc * bytes + crank * hbytes, hbytes,
+                           bar(B_W_FULL + stage));
+            }
+          }
+          src += layer_chunks(L) * bytes;
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ===================== MMA warp: the leader issues the pair's MMAs, the peer relays readiness ==========
+    if (lane == 0) {
+      uint32_t q = 0, lit = 0;
+      for (int itp = 0; itp < iters; ++itp) {
+        for (int L = 0; L < N_MMA_LAYERS; ++L, ++lit) {
+          const int nch = layer_chunks(L);
+          const uint32_t idesc = umma2_idesc(layer_n(L));
+          const bool stat = stationary(L);
+          const uint32_t qbase = q;
+          for (int tl = 0; tl < 2; ++tl) {
+            if (stat) q = qbase;  // tile B walks the same resident chunks
+            mbar_wait(bar(B_ACT_READY + tl), lit & 1);  // this CTA's operand written + accumulator drained
+            if (crank != 0) {
+              remote_arrive(bar(B_PEER_ACT + tl), 0);
+            } else {
+              mbar_wait(bar(B_PEER_ACT + tl), lit & 1);
+              tc_fence_after();
+              if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4)
+                reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + tl * 2] = clock64();
+            }
+            const uint32_t d_tmem = tmem_base + tl * 256;
+            for (int kc = 0; kc < nch; ++kc, ++q) {
+              const uint32_t stage = q % NST;
+              const bool first_use = !stat || tl == 0;
+              if (first_use) mbar_wait(bar(B_W_FULL + stage), (q / NST) & 1);
+              if (crank != 0) {
+                if (first_use) remote_arrive(bar(B_PEER_W + stage), 0);
+                continue;
+              }
+              if (first_use) mbar_wait(bar(B_PEER_W + stage), (q / NST) & 1);
+              tc_fence_after();
+              const uint32_t b_addr = sbase + OFF_W + stage * HALF_STAGE;
+              const bool from_enc = (L == 0) || (kc == 4);
+              const uint32_t a_addr = from_enc ? sbase + OFF_ENC + tl * CHUNK_A_BYTES
+                                               : sbase + OFF_ACT + tl * ACT_BYTES + kc * CHUNK_A_BYTES;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma2_bf16(d_tmem, umma_desc(a_addr + j * 32), umma_desc(b_addr + j * 32), idesc, (kc | j) != 0);
+              if (!stat || tl == 1) umma2_commit_mc(bar(B_W_EMPTY + stage), (uint16_t)3);  // slot free in BOTH CTAs
+            }
+            if (crank == 0) {
+              umma2_commit_mc(bar(B_ACC_FULL + tl), (uint16_t)3);     // wakes both CTAs' epilogue warps
+              if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4)
+                reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + tl * 2 + 1] = clock64();
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== 16 encode + epilogue warps, serving tile A and tile B alternately ==================
+    const int quad = warp & 3, quarter = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int quad_bar = 1 + quad;
+    const float* __restrict__ aux_g = reinterpret_cast<const float*>(aux_bytes_g);
+    RowSwz sw;
+    sw.row_off = row * 128;
+    sw.x4 = (row & 7) << 4;
+    const uint32_t tmem_q = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t it = 0;        // per-tile layer counter (acc_full / act_ready parity)
+    uint32_t bias_use[2] = {0, 0};
+    const bool loader = threadIdx.x == 0;
+    if (loader) {  // biases of layers 0 and 1 (1 KB each) into the two buffers
+      for (int b = 0; b < 2; ++b) {
+        mbar_expect_tx(bar(B_BIAS_FULL + b), 1024);
+        tma_bulk_g2s(sbase + OFF_BIAS + b * 1024, aux_bytes_g + b * (AUX_REC_FLOATS * 4), 1024, bar(B_BIAS_FULL + b));
+      }
+    }
+    for (int itp = 0; itp < iters; ++itp) {
+      const int pair = blockIdx.x + itp * (int)gridDim.x;
+      int64_t s_t[2];
+      bool valid_t[2];
+      int64_t ray_t[2];
+      // ---- positional encoding of both tiles' samples: this thread = one row, feature pairs 8*quarter .. +7 ----
+#pragma unroll
+      for (int tl = 0; tl < 2; ++tl) {
+        const int64_t s = ((int64_t)pair * 2 + tl) * TILE_M + row;
+        const bool valid = pair < P.num_pairs && s < P.total;
+        const int64_t sc = valid ? s : P.total - 1;
+        const int64_t ray = sc / P.p;
+        s_t[tl] = s;
+        valid_t[tl] = valid;
+        ray_t[tl] = ray;
+        const float4* rp = reinterpret_cast<const float4*>(P.rays + ray * 16);
+        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+        const float tt = __ldg(P.t + sc);
+        const float pc0 = __fmul_rn(r0.x, tt), pc1 = __fmul_rn(r0.y, tt), pc2 = __fmul_rn(r0.z, tt);
+        float pos[3];
+        pos[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.w, pc0), __fmul_rn(r1.x, pc1)), __fmul_rn(r1.y, pc2)), r3.x);
+        pos[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.z, pc0), __fmul_rn(r1.w, pc1)), __fmul_rn(r2.x, pc2)), r3.y);
+        pos[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.y, pc0), __fmul_rn(r2.z, pc1)), __fmul_rn(r2.w, pc2)), r3.z);
+        uint32_t f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pi = quarter * 8 + i;  // feature pair index = c*10 + l
+          if (pi < 30) {
+            const int c = pi / 10, l = pi % 10;
+            const float x = c == 0 ? pos[0] : (c == 1 ? pos[1] : pos[2]);
+            float sn, cs;
+            fast_sincos(__fmul_rn(__uint_as_float(c_tc_freq_point[l]), x), sn, cs);
+            f[i] = pack_bf16(sn, cs);
+          } else {
+            f[i] = 0u;  // K padded 60 -> 64
+          }
+        }
+        const uint32_t enc = sbase + OFF_ENC + tl * CHUNK_A_BYTES;
+        st_shared_v4(sw.addr(enc, quarter * 2), f[0], f[1], f[2], f[3]);
+        st_shared_v4(sw.addr(enc, quarter * 2 + 1), f[4], f[5], f[6], f[7]);
+        if (STASH && valid) {
+          uint4* d = reinterpret_cast<uint4*>(P.st_enc + s * 64 + quarter * 16);
+          d[0] = make_uint4(f[0], f[1], f[2], f[3]);
+          d[1] = make_uint4(f[4], f[5], f[6], f[7]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar(B_ACT_READY + tl));
+      }
+
+      for (int L = 0; L < N_MMA_LAYERS; ++L, ++it) {
+        const int bb = L & 1;
+        const uint32_t bias_s = sbase + OFF_BIAS + bb * 1024;
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl) {
+          const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
+          const uint32_t enc = sbase + OFF_ENC + tl * CHUNK_A_BYTES;
+          const uint32_t tmem_row = tmem_q + tl * 256;
+          mbar_wait(bar(B_ACC_FULL + tl), it & 1);
+          tc_fence_after();
+          if (tl == 0) mbar_wait(bar(B_BIAS_FULL + bb), bias_use[bb] & 1);
+          if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
+            reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 4 + tl * 2] = clock64();
+          if (L == 7)
+            epilogue_q<EPI_RELU_SIGMA, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+          else if (L == 8)
+            epilogue_q<EPI_LINEAR, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+          else if (L == 9)
+            epilogue_q<EPI_COLOUR, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+          else
+            epilogue_q<EPI_RELU, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+          if (L == 4) {
+            // the xyz features of this tile are dead (all its MMAs retired): store the view features in their place
+            if (quarter == 0) {
+              const float4* de = reinterpret_cast<const float4*>(P.dir_enc + ray_t[tl] * 24);
+              uint32_t f[12];
+#pragma unroll
+              for (int j = 0; j < 6; ++j) {
+                const float4 d4 = __ldg(de + j);
+                f[2 * j] = pack_bf16(d4.x, d4.y);
+                f[2 * j + 1] = pack_bf16(d4.z, d4.w);
+              }
+#pragma unroll
+              for (int j = 0; j < 3; ++j) st_shared_v4(sw.addr(enc, j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              st_shared_v4(sw.addr(enc, 3), 0u, 0u, 0u, 0u);
+              if (STASH && valid_t[tl]) {
+                uint4* d = reinterpret_cast<uint4*>(P.st_denc + s_t[tl] * 32);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) d[j] = make_uint4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                d[3] = make_uint4(0u, 0u, 0u, 0u);
+              }
+            } else if (quarter == 1) {
+#pragma unroll
+              for (int j = 4; j < 8; ++j) st_shared_v4(sw.addr(enc, j), 0u, 0u, 0u, 0u);
+            }
+          }
+          if (L != 9) {
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar(B_ACT_READY + tl));
+          }
+          if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
+            reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 5 + tl * 2] = clock64();
+        }
+        // both tiles are done with this layer's bias row: refill the buffer with layer L+2's (next pair's for L = 8, 9)
+        ++bias_use[bb];
+        asm volatile("bar.sync %0, %1;" ::"r"(BAR_ID_EPI_ALL), "r"(EPI_THREADS) : "memory");
+        if (loader) {
+          const int Ln = (L + 2) % N_MMA_LAYERS;
+          const bool more = (L + 2 < N_MMA_LAYERS) || (itp + 1 < iters);
+          if (more) {
+            fence_proxy_async();
+            mbar_expect_tx(bar(B_BIAS_FULL + bb), 1024);
+            tma_bulk_g2s(sbase + OFF_BIAS + bb * 1024, aux_bytes_g + Ln * (AUX_REC_FLOATS * 4), 1024, bar(B_BIAS_FULL + bb));
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    tmem2_dealloc_512(tmem_base);
+  }
+}
+
+}  // namespace v7
+
 // ---------------------------------------------------------------------------------------------------------
 // weight packing: nn.Linear (out,in) fp32 -> bf16 [N x 64] SW128 K-chunks in consumption order
 // ---------------------------------------------------------------------------------------------------------
@@ -690,6 +1507,40 @@ static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const fl
   P.num_pairs = (int)((tiles + 1) / 2);
   if (P.num_pairs == 0) return NT_OK;
   int grid = ctx->sm_count < P.num_pairs ? ctx->sm_count : P.num_pairs;
+  // schedule variants (NT_OPT_MLP_TC_VERSION / env NT_MLP_TC_VERSION): 5 = tile pair in lock-step (default, fastest),
+  // 6 = staggered tiles + 2-CTA weight multicast, 7 = staggered tiles + cta_group::2 MMAs with layer-stationary weights
+  int ver = ctx->opt_tc_version;
+  if (ver == 0) {
+    const char* e = getenv("NT_MLP_TC_VERSION");
+    ver = e ? atoi(e) : 5;
+  }
+  const bool use_v6 = ver == 6, use_v7 = ver == 7;
+  if (use_v7 && (!dbg || dbg_layer >= 100) && !stash) {
+    static bool set7 = false;
+    if (!set7) {
+      NT_CUDA(cudaFuncSetAttribute(v7::mlp_tc7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::SMEM7_BYTES));
+      set7 = true;
+    }
+    int g7 = ctx->sm_count & ~1;                       // whole 2-CTA clusters
+    const int need = ((P.num_pairs + 1) / 2) * 2;
+    if (g7 > need) g7 = need;
+    v7::mlp_tc7_kernel<false><<<g7, N_THREADS, v7::SMEM7_BYTES, st>>>(P);
+    NT_LAUNCH_CHECK(ctx);
+    return NT_OK;
+  }
+  if (use_v6 && (!dbg || dbg_layer >= 100) && !stash) {
+    static bool set6 = false;
+    if (!set6) {
+      NT_CUDA(cudaFuncSetAttribute(v6::mlp_tc6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v6::SMEM6_BYTES));
+      set6 = true;
+    }
+    int g6 = ctx->sm_count & ~1;                       // whole 2-CTA clusters
+    const int need = ((P.num_pairs + 1) / 2) * 2;
+    if (g6 > need) g6 = need;
+    v6::mlp_tc6_kernel<false><<<g6, N_THREADS, v6::SMEM6_BYTES, st>>>(P);
+    NT_LAUNCH_CHECK(ctx);
+    return NT_OK;
+  }
   if (stash)
     mlp_tc_kernel<false, true><<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
   else if (dbg)

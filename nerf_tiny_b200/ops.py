@@ -43,6 +43,9 @@ class Context:
     def _f(self, *shape):
         return torch.empty(*shape, dtype=torch.float32, device=self.dev)
 
+    def set_option(self, key, value):
+        _lib.check(self.lib.nt_set_option(self.h, key, value))
+
     @property
     def launches(self):
         return int(self.lib.nt_launch_count(self.h))

@@ -564,3 +564,27 @@ def test_training_psnr_parity(dev, golden_dir, prec):
                                      ref_samples.std(ddof=1), len(ref_samples), delta, se))
     assert abs(first_loss - ref_loss[0]) <= (1e-4 if prec == "fp32" else 2e-3) * ref_loss[0]      # step 0 is deterministic
     assert abs(delta) <= 0.1 + 2 * se
+
+
+@pytest.mark.parametrize("version", [5, 6, 7])
+def test_mlp_bf16_schedule_variants(ctx, dev, golden_dir, version):
+    """The three schedules of the fused tcgen05 kernel (lock-step pair / cluster multicast / cta_group::2) agree with the
+    fp32 CUDA path on a launch large enough to give every CTA several tile pairs, plus a ragged tail."""
+    g = load(golden_dir, "fern64")
+    flat = flat_of(sd_of("trained64"), dev)
+    packed = ctx.pack(flat, BF16)
+    reps = 40                                                    # 64 rays x 40 = 2560 rays
+    row = cu(np.tile(g["row"], reps)[:2501], dev)
+    col = cu(np.tile(g["col"], reps)[:2501], dev)
+    c2w = cu(np.tile(g["c2w"], (reps, 1, 1))[:2501], dev)
+    rays, _, de = ctx.raygen(row, col, c2w, cu(g["k_inv"], dev))
+    t = cu(np.tile(g["t_fine"], (reps, 1))[:2501], dev)
+    r32, s32, _ = ctx.mlp_forward(FP32, t, rays, de, flat)
+    ctx.set_option(2, version)
+    try:
+        r16, s16, _ = ctx.mlp_forward(BF16, t, rays, de, flat, packed)
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_option(2, 0)
+    assert float((r32 - r16).abs().max()) <= 1e-2
+    assert float((s32 - s16).abs().max()) <= 3e-2 * max(1.0, float(s32.abs().max()))
