@@ -167,3 +167,7 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
                                void* ws, size_t ws_bytes, cudaStream_t st);
 int nt_launch_dw_gemm(nt_ctx* ctx, int S, const void* G, int ldg, int m_valid, const void* H, int ldh, int n_valid,
                       float* C, int ldc, cudaStream_t st);
+// grouped weight-gradient GEMM: queue problems of one backward pass (all with the same sample count S), flush once
+int nt_dw_group_begin(int S);
+int nt_dw_group_add(const void* G, int ldg, int m_valid, const void* H, int ldh, int n_valid, float* C, int ldc);
+int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st);

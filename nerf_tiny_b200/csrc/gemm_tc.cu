@@ -543,6 +543,122 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Grouped weight-gradient GEMM: every dW of one backward pass (14 problems: 10 tensor-core layers, the two
+// concatenation tails and the two heads) in ONE launch.  Each problem gets a slice of the grid proportional to its
+// HBM traffic and is split over the sample axis inside its slice, so a [256 x 256] gradient receives ~14 atomic
+// partial sums instead of 148 and the launch runs at HBM speed instead of atomic speed.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DWG_MAX = 16;
+struct DwGroup {
+  CUtensorMap map_a[DWG_MAX];
+  CUtensorMap map_b[DWG_MAX];
+  float* C[DWG_MAX];
+  int ldc[DWG_MAX], m_valid[DWG_MAX], n_valid[DWG_MAX];
+  int cta_begin[DWG_MAX + 1];  // grid slice of every problem
+  int kb_per_cta[DWG_MAX];
+  int n_problems;
+  int S;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) dw_grouped_kernel(const __grid_constant__ DwGroup g) {
+  constexpr int BN = 256;
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE = DW_A_BYTES + B_BYTES;
+  constexpr int OFF_BAR = DW_STAGES * STAGE;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };  // full[3] 0-2, empty[3] 3-5, acc_full 6
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
+  int pr = 0;
+  while (pr + 1 < g.n_problems && (int)blockIdx.x >= g.cta_begin[pr + 1]) ++pr;
+  const int slot = blockIdx.x - g.cta_begin[pr];
+  const int kb_total = g.S / BK;
+  const int kb0 = slot * g.kb_per_cta[pr];
+  const int kb1 = min(kb_total, kb0 + g.kb_per_cta[pr]);
+  const int m_valid = g.m_valid[pr], n_valid = g.n_valid[pr];
+  const int a_boxes = (m_valid + 63) / 64, b_boxes = (n_valid + 63) / 64;  // boxes that are not entirely out of range
+  const bool two_m = m_valid > 128;
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023) __trap();
+    for (int s = 0; s < DW_STAGES; ++s) {
+      mbar_init(bar(s), 1);
+      mbar_init(bar(3 + s), 1);
+    }
+    mbar_init(bar(6), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++q) {
+        const uint32_t s = q % DW_STAGES;
+        mbar_wait(bar(3 + s), ((q / DW_STAGES) & 1) ^ 1);
+        mbar_expect_tx(bar(s), (a_boxes + b_boxes) * 8192);
+        const uint32_t da = sbase + s * STAGE, db = da + DW_A_BYTES;
+        for (int b = 0; b < a_boxes; ++b) tma_load_2d(da + b * 8192, &g.map_a[pr], b * 64, kb * BK, bar(s));
+        for (int b = 0; b < b_boxes; ++b) tma_load_2d(db + b * 8192, &g.map_b[pr], b * 64, kb * BK, bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // N of the instruction = the columns that exist (multiple of 64): columns beyond were never loaded
+      const uint32_t idesc = idesc_bf16(b_boxes * 64, true);
+      uint32_t q = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++q) {
+        const uint32_t s = q % DW_STAGES;
+        mbar_wait(bar(s), (q / DW_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = sbase + s * STAGE, b_addr = a_addr + DW_A_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t bd = desc_mnmajor(b_addr + j * 2048, 8192);
+          const uint32_t acc = (kb > kb0 || j > 0) ? 1u : 0u;
+          umma_bf16(tmem_base, desc_mnmajor(a_addr + j * 2048, 8192), bd, idesc, acc);
+          if (two_m) umma_bf16(tmem_base + 256, desc_mnmajor(a_addr + 16384 + j * 2048, 8192), bd, idesc, acc);
+        }
+        umma_commit(bar(3 + s));
+      }
+      umma_commit(bar(6));
+    }
+  } else if (kb1 > kb0) {
+    const int e = warp - 2, quad = warp & 3, half = e >> 2;
+    mbar_wait(bar(6), 0);
+    tc_fence_after();
+    float* Cp = g.C[pr];
+    const int ldc = g.ldc[pr];
+    for (int mt = 0; mt < (two_m ? 2 : 1); ++mt) {
+      const int m = mt * 128 + quad * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + mt * 256;
+      for (int i = 0; i < 4; ++i) {
+        const int n0 = (half * 4 + i) * 32;
+        if (n0 >= b_boxes * 64) continue;  // warp-uniform: these columns were not computed
+        uint32_t raw[32];
+        tmem_ld32(trow + n0, raw);
+        if (m < m_valid && n0 < n_valid) red_add_32(Cp + (int64_t)m * ldc + n0, raw, n_valid - n0);
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
 // ---- host side: tensor maps ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -690,5 +806,71 @@ int nt_launch_dw_gemm(nt_ctx* ctx, int S, const void* G, int ldg, int m_valid, c
   if (BN == 64) DW_LAUNCH(64) else if (BN == 128) DW_LAUNCH(128) else DW_LAUNCH(256)
 #undef DW_LAUNCH
   NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
+
+// ---- grouped dW: problems are queued during the backward pass and flushed in one launch ---------------------------
+struct DwQueue {
+  DwGroup g;
+  int weight[DWG_MAX];
+};
+static thread_local DwQueue g_dwq;
+
+int nt_dw_group_begin(int S) {
+  if (S <= 0 || S % BK != 0) {
+    nt_set_error("dw_group: S must be a positive multiple of 64");
+    return NT_ERR_INVALID;
+  }
+  g_dwq.g.n_problems = 0;
+  g_dwq.g.S = S;
+  return NT_OK;
+}
+
+int nt_dw_group_add(const void* G, int ldg, int m_valid, const void* H, int ldh, int n_valid, float* C, int ldc) {
+  DwGroup& g = g_dwq.g;
+  if (g.n_problems >= DWG_MAX || m_valid > 256 || n_valid > 256 || m_valid <= 0 || n_valid <= 0) {
+    nt_set_error("dw_group: too many problems or bad shape");
+    return NT_ERR_INVALID;
+  }
+  const int i = g.n_problems;
+  int rc;
+  if ((rc = make_map(&g.map_a[i], G, g.S, m_valid, ldg, 64, BK)) != NT_OK) return rc;
+  if ((rc = make_map(&g.map_b[i], H, g.S, n_valid, ldh, 64, BK)) != NT_OK) return rc;
+  g.C[i] = C;
+  g.ldc[i] = ldc;
+  g.m_valid[i] = m_valid;
+  g.n_valid[i] = n_valid;
+  g_dwq.weight[i] = ((m_valid + 63) / 64 + (n_valid + 63) / 64);  // 64-wide boxes moved per sample block
+  g.n_problems = i + 1;
+  return NT_OK;
+}
+
+int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st) {
+  DwGroup& g = g_dwq.g;
+  if (g.n_problems == 0) return NT_OK;
+  const int kb_total = g.S / BK;
+  int wsum = 0;
+  for (int i = 0; i < g.n_problems; ++i) wsum += g_dwq.weight[i];
+  const int budget = 2 * ctx->sm_count;  // two CTAs' worth of work per SM keeps the tail short
+  int begin = 0;
+  for (int i = 0; i < g.n_problems; ++i) {
+    int ctas = (int)((long long)budget * g_dwq.weight[i] / wsum);
+    if (ctas < 1) ctas = 1;
+    if (ctas > kb_total) ctas = kb_total;
+    g.kb_per_cta[i] = (kb_total + ctas - 1) / ctas;
+    ctas = (kb_total + g.kb_per_cta[i] - 1) / g.kb_per_cta[i];
+    g.cta_begin[i] = begin;
+    begin += ctas;
+  }
+  g.cta_begin[g.n_problems] = begin;
+  constexpr int smem = DW_STAGES * (DW_A_BYTES + 256 * 128) + 128;
+  static bool set = false;
+  if (!set) {
+    NT_CUDA(cudaFuncSetAttribute(dw_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    set = true;
+  }
+  dw_grouped_kernel<<<begin, GEMM_THREADS, smem, st>>>(g);
+  NT_LAUNCH_CHECK(ctx);
+  g.n_problems = 0;
   return NT_OK;
 }

@@ -17,7 +17,7 @@ typedef __nv_bfloat16 bf16;
 struct Ws {
   TcStash st;
   float* rgb;
-  bf16 *GA, *GB, *Gu, *Gz, *Gzs, *WT;
+  bf16 *GI, *GS[8], *Gu, *Gz, *Gzs, *WT;  // GI = d point_info, GS[i] = d pre-activation of trunk layer i
   float *gzsig, *genc;
   size_t bytes;
 };
@@ -45,8 +45,8 @@ Ws carve(void* base, int64_t S) {
   w.st.denc = take(S * 32 * 2);
   w.st.zsig = (float*)take(S * 4);
   w.rgb = (float*)take(S * 12);
-  w.GA = (bf16*)take(S * 256 * 2);
-  w.GB = (bf16*)take(S * 256 * 2);
+  w.GI = (bf16*)take(S * 256 * 2);
+  for (int i = 0; i < 8; ++i) w.GS[i] = (bf16*)take(S * 256 * 2);
   w.Gu = (bf16*)take(S * 128 * 2);
   w.Gz = (bf16*)take(S * 8 * 2);
   w.Gzs = (bf16*)take(S * 8 * 2);
@@ -261,8 +261,10 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
                                                                      G + T.b[L_COLOR], G + T.b[L_SIGMA]);
   NT_LAUNCH_CHECK(ctx);
 
+  // every weight gradient of this pass is queued and computed by ONE grouped tensor-core launch at the end
+  NT_TRY(nt_dw_group_begin(S));
   auto dW = [&](const bf16* Gm, int ldg, int M, const bf16* Hm, int ldh, int N, float* dst, int ldc) {
-    return nt_launch_dw_gemm(ctx, S, Gm, ldg, M, Hm, ldh, N, dst, ldc, st);
+    return nt_dw_group_add(Gm, ldg, M, Hm, ldh, N, dst, ldc);
   };
   // dX also accumulates the column sums of what it stores = the bias gradient of the layer that produced `mask`
   auto dX = [&](const bf16* Gm, int ldg, int K, const bf16* WTm, int N, bf16* out, const bf16* mask, const float* r1_row,
@@ -284,15 +286,14 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
   NT_TRY(dW(w.Gu, 128, 128, DENC, 32, 24, G + T.w[L_DIR], 280));
   NT_TRY(dW(w.Gu, 128, 128, H[8], 256, 256, G + T.w[L_DIR] + 24, 280));
   NT_TRY(colsum_bf16(ctx, w.Gu, S, 128, 128, G + T.b[L_DIR], st));
-  NT_TRY(dX(w.Gu, 128, 128, w.WT + WT_DIRINFO, 256, w.GA, nullptr, nullptr, nullptr, G + T.b[L_INFO]));  // g_info
+  NT_TRY(dX(w.Gu, 128, 128, w.WT + WT_DIRINFO, 256, w.GI, nullptr, nullptr, nullptr, G + T.b[L_INFO]));  // g_info
   // point_info (256 -> 256, linear) and the sigma head (256 -> 1, abs)
-  NT_TRY(dW(w.GA, 256, 256, H[7], 256, 256, G + T.w[L_INFO], 256));
+  NT_TRY(dW(w.GI, 256, 256, H[7], 256, 256, G + T.w[L_INFO], 256));
   NT_TRY(dW(w.Gzs, 8, 1, H[7], 256, 256, G + T.w[L_SIGMA], 256));
   // g_pre7 = relu'(h7) * (g_info . W_p + g_zsig (x) w_sigma)
-  NT_TRY(dX(w.GA, 256, 256, w.WT + WT_INFO, 256, w.GB, H[7], w.gzsig, P + T.w[L_SIGMA], G + T.b[L_P7]));
-  bf16* cur = w.GB;
-  bf16* nxt = w.GA;
+  NT_TRY(dX(w.GI, 256, 256, w.WT + WT_INFO, 256, w.GS[7], H[7], w.gzsig, P + T.w[L_SIGMA], G + T.b[L_P7]));
   for (int i = 7; i >= 1; --i) {
+    bf16* cur = w.GS[i];
     NT_TRY(dW(cur, 256, 256, H[i - 1], 256, 256, G + T.w[i], kLayerIn[i]));
     if (i == 4) {
       NT_TRY(dW(cur, 256, 256, ENC, 64, 60, G + T.w[L_P4] + 256, 316));
@@ -304,19 +305,17 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
         NT_TRY(nt_launch_gemm_tc(ctx, 0, S, 64, 256, cur, 256, w.WT + WT_ENC4, 256, e, st));
       }
     }
-    NT_TRY(dX(cur, 256, 256, w.WT + WT_TRUNK + (i - 1) * 65536, 256, nxt, H[i - 1], nullptr, nullptr, G + T.b[i - 1]));
-    bf16* tmp = cur;
-    cur = nxt;
-    nxt = tmp;
+    NT_TRY(dX(cur, 256, 256, w.WT + WT_TRUNK + (i - 1) * 65536, 256, w.GS[i - 1], H[i - 1], nullptr, nullptr, G + T.b[i - 1]));
   }
-  NT_TRY(dW(cur, 256, 256, ENC, 64, 60, G + T.w[L_P0], 60));
+  NT_TRY(dW(w.GS[0], 256, 256, ENC, 64, 60, G + T.w[L_P0], 60));
   if (g_t) {
     GemmTcEpi e = epi0();
     e.C = w.genc;
     e.ldc = 64;
     e.atomic_f32 = 1;  // accumulate onto the skip-connection part
-    NT_TRY(nt_launch_gemm_tc(ctx, 0, S, 64, 256, cur, 256, w.WT + WT_ENC0, 256, e, st));
+    NT_TRY(nt_launch_gemm_tc(ctx, 0, S, 64, 256, w.GS[0], 256, w.WT + WT_ENC0, 256, e, st));
     NT_TRY(nt_launch_encode_backward(ctx, n, p, t, rays, w.genc, 64, g_t, st));
   }
+  NT_TRY(nt_dw_group_flush(ctx, st));
   return NT_OK;
 }
