@@ -1,6 +1,7 @@
 // Shared declarations for libnerftiny (sm_100a).  Host+device helpers, the layer table and
 // the internal launch functions each .cu file exports to api.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -171,3 +172,4 @@ int nt_launch_dw_gemm(nt_ctx* ctx, int S, const void* G, int ldg, int m_valid, c
 int nt_dw_group_begin(int S);
 int nt_dw_group_add(const void* G, int ldg, int m_valid, const void* H, int ldh, int n_valid, float* C, int ldc);
 int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st);
+int nt_make_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);

@@ -874,3 +874,8 @@ int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st) {
   g.n_problems = 0;
   return NT_OK;
 }
+
+// 2-D bf16 tensor map [rows][cols] (row pitch ld elements), box = box_cols x box_rows, SWIZZLE_128B (shared with mlp_tc.cu)
+int nt_make_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  return make_map(map, base, rows, cols, ld, box_cols, box_rows);
+}

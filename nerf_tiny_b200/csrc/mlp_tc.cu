@@ -13,6 +13,7 @@
 //     bf16 and write the next layer's A operand in place; the sigma head (256->1, abs) and colour head (128->3,
 //     sigmoid) are evaluated on CUDA cores from the fp32 accumulators in the same pass.
 // Skip (nerf.py:109) and view (nerf.py:118) concatenations are extra K-chunks accumulated into the same TMEM tile.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
@@ -78,8 +79,13 @@ struct TcParams {
   // training stash (STASH instantiation): bf16 activations kept in HBM for the layer-major backward
   __nv_bfloat16* st[N_MMA_LAYERS];  // post-activation output of every tensor-core layer, [S][256] ([S][128] for dir_info)
   __nv_bfloat16* st_enc;            // xyz features [S][64] (60 + zero pad)
-  __nv_bfloat16* st_denc;           // view features [S][32] (24 + zero pad)
+  __nv_bfloat16* st_denc;           // view features [S][64] (24 + zero pad)
   float* st_zsig;                   // sigma pre-activation [S] (abs' needs the sign)
+  // v5 STASH instantiation: the operand tiles already sit in shared memory in the SWIZZLE_128B layout, so the stash
+  // of layers 0..8, the xyz features and the view features is written by TMA tensor stores (box 64 cols x 128 rows),
+  // not by the epilogue threads.  maps 0..8 = st[0..8] ([S][256]), 9 = st_enc, 10 = st_denc ([S][64]).
+  CUtensorMap st_map[11];
+  int use_tma_stash;
 };
 
 __constant__ uint32_t c_tc_freq_point[10] = NT_FREQ_POINT_INIT;
@@ -123,6 +129,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(src)
                : "memory");
 }
 
@@ -323,7 +335,8 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
           w[e] = KIND == EPI_LINEAR ? pack_bf16(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1])
                                     : pack_bf16_relu(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1]);
         st_shared_v4(sw.addr(dst, (cb & 1) * 4 + qd), w[0], w[1], w[2], w[3]);
-        if (STASH && valid) *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (STASH && !P.use_tma_stash && valid)
+          *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }
@@ -356,7 +369,7 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
 template <bool DBG, bool STASH>
-__global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) {
+__global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -421,6 +434,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
                 mbar_wait(bar(BAR_ACT_READY + tl), lit & 1);
                 tc_fence_after();
                 TC_PROF(tl);
+                if (STASH && P.use_tma_stash) {
+                  // this layer's operand = the previous layer's bf16 output (or the features): stash it from smem
+                  const int row0 = (pair * 2 + tl) * TILE_M;
+                  if (row0 < P.total) {
+                    if (L == 0) {
+                      tma_store_2d(&P.st_map[9], 0, row0, sbase + OFF_ENC + tl * CHUNK_A_BYTES);
+                    } else {
+#pragma unroll
+                      for (int c = 0; c < 4; ++c)
+                        tma_store_2d(&P.st_map[L - 1], c * 64, row0, sbase + OFF_ACT + tl * ACT_BYTES + c * CHUNK_A_BYTES);
+                      if (L == 9) tma_store_2d(&P.st_map[10], 0, row0, sbase + OFF_ENC + tl * CHUNK_A_BYTES);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                  }
+                }
                 if (tl == 1) {
                   // every epilogue thread is done with the previous layer's record: stage this layer's biases / head
                   // weights (1-2.5 KB) for the epilogue that follows these MMAs
@@ -436,7 +464,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
 #pragma unroll
               for (int j = 0; j < 4; ++j)  // 4 x (K = 16) inside the 64-wide swizzled chunk: +32 B per step
                 umma_bf16(d_tmem, umma_desc(a_addr + j * 32), umma_desc(b_addr + j * 32), idesc, (kc | j) != 0);
-              if (kc == nch - 1) umma_commit(bar(BAR_ACC_FULL + tl));
+              if (kc == nch - 1) {
+                // the epilogue that this commit releases overwrites the operand tiles: TMA stash reads must be done
+                if (STASH && P.use_tma_stash) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                umma_commit(bar(BAR_ACC_FULL + tl));
+              }
             }
             umma_commit(bar(BAR_W_EMPTY + stage));  // frees the ring slot once both tiles' MMAs retire
             if (kc == 0) TC_PROF(2);
@@ -444,6 +476,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
           }
         }
       }
+      if (STASH && P.use_tma_stash) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else {
     // ===================== encode + epilogue warps: per tile 4 lane quadrants x 2 column halves =============
@@ -494,7 +527,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           st_shared_v4(sw.addr(enc, half * 4 + j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        if (STASH && valid) {
+        if (STASH && !P.use_tma_stash && valid) {
           uint4* d = reinterpret_cast<uint4*>(P.st_enc + s * 64 + half * 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j) d[j] = make_uint4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -532,11 +565,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const TcParams P) 
 #pragma unroll
             for (int j = 0; j < 3; ++j) st_shared_v4(sw.addr(enc, j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             st_shared_v4(sw.addr(enc, 3), 0u, 0u, 0u, 0u);
-            if (STASH && valid) {
-              uint4* d = reinterpret_cast<uint4*>(P.st_denc + s * 32);
+            if (STASH && !P.use_tma_stash && valid) {
+              uint4* d = reinterpret_cast<uint4*>(P.st_denc + s * 64);
 #pragma unroll
               for (int j = 0; j < 3; ++j) d[j] = make_uint4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-              d[3] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+              for (int j = 3; j < 8; ++j) d[j] = make_uint4(0u, 0u, 0u, 0u);
             }
           } else {
 #pragma unroll
@@ -1491,6 +1525,16 @@ static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const fl
     P.st_enc = (__nv_bfloat16*)stash->enc;
     P.st_denc = (__nv_bfloat16*)stash->denc;
     P.st_zsig = stash->zsig;
+    const int64_t S = n * p;
+    for (int i = 0; i < 9; ++i) {
+      int rc = nt_make_map_bf16(&P.st_map[i], stash->layer[i], S, 256, 256, 64, TILE_M);
+      if (rc != NT_OK) return rc;
+    }
+    int rc = nt_make_map_bf16(&P.st_map[9], stash->enc, S, 64, 64, 64, TILE_M);
+    if (rc != NT_OK) return rc;
+    rc = nt_make_map_bf16(&P.st_map[10], stash->denc, S, 64, 64, 64, TILE_M);
+    if (rc != NT_OK) return rc;
+    P.use_tma_stash = getenv("NT_NO_TMA_STASH") ? 0 : 1;
   }
   P.t = t;
   P.rays = rays;

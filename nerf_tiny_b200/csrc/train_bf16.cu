@@ -42,7 +42,7 @@ Ws carve(void* base, int64_t S) {
   for (int i = 0; i < 9; ++i) w.st.layer[i] = take(S * 256 * 2);
   w.st.layer[9] = take(S * 128 * 2);
   w.st.enc = take(S * 64 * 2);
-  w.st.denc = take(S * 32 * 2);
+  w.st.denc = take(S * 64 * 2);
   w.st.zsig = (float*)take(S * 4);
   w.rgb = (float*)take(S * 12);
   w.GI = (bf16*)take(S * 256 * 2);
@@ -283,7 +283,7 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
   // colour layer (128 -> 3)
   NT_TRY(dW(w.Gz, 8, 3, H[9], 128, 128, G + T.w[L_COLOR], 128));
   // dir_info on [dir_enc | point_info] (nerf.py:118)
-  NT_TRY(dW(w.Gu, 128, 128, DENC, 32, 24, G + T.w[L_DIR], 280));
+  NT_TRY(dW(w.Gu, 128, 128, DENC, 64, 24, G + T.w[L_DIR], 280));
   NT_TRY(dW(w.Gu, 128, 128, H[8], 256, 256, G + T.w[L_DIR] + 24, 280));
   NT_TRY(colsum_bf16(ctx, w.Gu, S, 128, 128, G + T.b[L_DIR], st));
   NT_TRY(dX(w.Gu, 128, 128, w.WT + WT_DIRINFO, 256, w.GI, nullptr, nullptr, nullptr, G + T.b[L_INFO]));  // g_info
