@@ -1,0 +1,450 @@
+// Fused backward-data chain of the 8x256 MLP on tcgen05 (NT_PREC_BF16 training): the mirror image of mlp_tc.cu.
+// Autograd of Network.forward (nerf.py:101-124) w.r.t. the activations, SURVEY.md B.6/B.7:
+//   step 0 : g_info = g_u . W_d[:, 24:]                                   (dir_info -> point_info, no activation)
+//   step 1 : g_7    = relu'(h7) * (g_info . W_p + g_zsigma (x) w_sigma)    (point_info and the sigma head join here)
+//   step k : g_{8-k} = relu'(h_{8-k}) * (g_{9-k} . W_{9-k}[:, :256])       k = 2..8  (trunk layers 7..1)
+// One persistent CTA per SM, pairs of 128-sample tiles in lock-step exactly like the forward kernel: the gradient tile
+// stays in shared memory as the bf16 SWIZZLE_128B A operand of the next step, transposed weights stream through a
+// 2-stage TMA ring in pre-packed K-chunks, accumulators live in TMEM.  The epilogue applies the ReLU' BIT mask that the
+// forward pass stashed (32 B per sample-layer instead of re-reading 512 B of activations), accumulates the bias
+// gradient (column sums by shuffle recursive-halving) and writes the next operand in place; every step's gradient
+// tile is also stashed to HBM by TMA tensor stores for the grouped weight-gradient GEMM (gemm_tc.cu).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int CHUNK_A_BYTES = TILE_M * 128;
+constexpr int ACT_BYTES = 4 * CHUNK_A_BYTES;
+constexpr int W_STAGE_BYTES = 256 * 128;
+constexpr int N_STAGES = 2;
+constexpr int N_STEPS = 9;
+constexpr int OFF_ACT = 0;
+constexpr int OFF_W = 2 * ACT_BYTES;
+constexpr int OFF_BAR = OFF_W + N_STAGES * W_STAGE_BYTES;
+constexpr int OFF_WSIG = OFF_BAR + 128;  // w_sigma row, fp32 [256]
+constexpr int SMEM_BYTES = OFF_WSIG + 1024;
+constexpr int N_THREADS = 576;  // 16 epilogue warps + TMA producer + MMA issuer
+constexpr int WARP_TMA = 16, WARP_MMA = 17;
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 2, BAR_ACC_FULL = 4, BAR_ACT_READY = 6, BAR_A_FULL = 8 };
+
+__host__ __device__ constexpr int step_chunks(int st) { return st == 0 ? 2 : 4; }
+constexpr int total_chunks() {
+  int c = 0;
+  for (int st = 0; st < N_STEPS; ++st) c += step_chunks(st);
+  return c;
+}
+constexpr int PACKED_BWD_BYTES = total_chunks() * W_STAGE_BYTES;  // 34 x 32 KB
+
+struct BwdParams {
+  CUtensorMap map_gu;             // load:  g_u  [S][128]
+  CUtensorMap map_out[N_STEPS];   // store: g_info, g_7 .. g_0  [S][256]
+  const uint8_t* packed;          // transposed bf16 weights in consumption order
+  const uint32_t* bits;           // ReLU' bit masks [8][S][8] (layer, sample, 256 bits)
+  const float* gzsig;             // [S]
+  const float* wsig;              // [256] fp32 (flat parameter buffer)
+  float* db[N_STEPS];             // bias gradients: point_info, layer 7 .. layer 0
+  int64_t total;
+  int num_pairs;
+};
+
+// ---- PTX wrappers (same conventions as mlp_tc.cu) ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins == 1024) t0 = clock64();
+    if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();  // never hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_constant__ BwdParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 96);
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023) __trap();
+    for (int s = 0; s < N_STAGES; ++s) {
+      mbar_init(bar(BAR_W_FULL + s), 1);
+      mbar_init(bar(BAR_W_EMPTY + s), 1);
+    }
+    for (int tl = 0; tl < 2; ++tl) {
+      mbar_init(bar(BAR_ACC_FULL + tl), 1);
+      mbar_init(bar(BAR_ACT_READY + tl), 2 * TILE_M);
+      mbar_init(bar(BAR_A_FULL + tl), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // w_sigma row for the rank-1 term of step 1
+  if (threadIdx.x < 256) reinterpret_cast<float*>(smem + OFF_WSIG)[threadIdx.x] = P.wsig[threadIdx.x];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == WARP_TMA) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
+        const uint8_t* src = P.packed;
+        for (int st = 0; st < N_STEPS; ++st)
+          for (int kc = 0; kc < step_chunks(st); ++kc, ++q) {
+            const uint32_t stage = q & 1;
+            mbar_wait(bar(BAR_W_EMPTY + stage), ((q >> 1) & 1) ^ 1);
+            mbar_expect_tx(bar(BAR_W_FULL + stage), W_STAGE_BYTES);
+            tma_bulk_g2s(sbase + OFF_W + stage * W_STAGE_BYTES, src, W_STAGE_BYTES, bar(BAR_W_FULL + stage));
+            src += W_STAGE_BYTES;
+          }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ===================== MMA issuer (+ operand loads / gradient stash by TMA) =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(256);
+      uint32_t q = 0, lit = 0, pl = 0;
+      int prev_pair = -1;
+      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pl) {
+        for (int st = 0; st < N_STEPS; ++st, ++lit) {
+          const int nch = step_chunks(st);
+          for (int kc = 0; kc < nch; ++kc, ++q) {
+            const uint32_t stage = q & 1;
+            mbar_wait(bar(BAR_W_FULL + stage), (q >> 1) & 1);
+            tc_fence_after();
+            const uint32_t b_addr = sbase + OFF_W + stage * W_STAGE_BYTES;
+#pragma unroll
+            for (int tl = 0; tl < 2; ++tl) {
+              const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
+              if (kc == 0) {
+                mbar_wait(bar(BAR_ACT_READY + tl), lit & 1);  // epilogue done: operand in place, accumulator drained
+                tc_fence_after();
+                const int row0 = (pair * 2 + tl) * TILE_M;
+                if (st == 0) {
+                  // stash the previous pair's last gradient tile (g_0), then fetch this pair's g_u tile
+                  if (prev_pair >= 0) {
+                    const int prow0 = (prev_pair * 2 + tl) * TILE_M;
+                    if (prow0 < P.total) {
+#pragma unroll
+                      for (int c = 0; c < 4; ++c) tma_store_2d(&P.map_out[N_STEPS - 1], c * 64, prow0, act + c * CHUNK_A_BYTES);
+                      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                  }
+                  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                  mbar_expect_tx(bar(BAR_A_FULL + tl), 2 * CHUNK_A_BYTES);
+                  tma_load_2d(act, &P.map_gu, 0, row0, bar(BAR_A_FULL + tl));
+                  tma_load_2d(act + CHUNK_A_BYTES, &P.map_gu, 64, row0, bar(BAR_A_FULL + tl));
+                  mbar_wait(bar(BAR_A_FULL + tl), pl & 1);
+                } else if (row0 < P.total) {
+                  // the operand of this step is the output of step st-1: stash it for the weight-gradient GEMM
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) tma_store_2d(&P.map_out[st - 1], c * 64, row0, act + c * CHUNK_A_BYTES);
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+              }
+              const uint32_t a_addr = act + kc * CHUNK_A_BYTES;
+              const uint32_t d_tmem = tmem_base + tl * 256;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_bf16(d_tmem, umma_desc(a_addr + j * 32), umma_desc(b_addr + j * 32), idesc, (kc | j) != 0);
+              if (kc == nch - 1) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // epilogue will overwrite the operand tile
+                umma_commit(bar(BAR_ACC_FULL + tl));
+              }
+            }
+            umma_commit(bar(BAR_W_EMPTY + stage));
+          }
+        }
+        prev_pair = pair;
+      }
+      // the last pair's g_0 tiles
+      if (prev_pair >= 0) {
+        for (int tl = 0; tl < 2; ++tl) {
+          mbar_wait(bar(BAR_ACT_READY + tl), lit & 1);
+          const int prow0 = (prev_pair * 2 + tl) * TILE_M;
+          if (prow0 < P.total) {
+            const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_store_2d(&P.map_out[N_STEPS - 1], c * 64, prow0, act + c * CHUNK_A_BYTES);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    // ===================== epilogue warps: per tile 4 lane quadrants x 2 column halves =====================
+    const int tl = (warp >> 2) & 1;
+    const int half = warp >> 3;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + tl * 256;
+    const uint32_t row_off = row * 128, x4 = (row & 7) << 4;
+    const uint32_t wsig_s = sbase + OFF_WSIG;
+    uint32_t it = 0;
+    mbar_arrive(bar(BAR_ACT_READY + tl));  // nothing to protect before the first pair
+    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
+      const int64_t s = ((int64_t)pair * 2 + tl) * TILE_M + row;
+      const bool valid = s < P.total;
+      const float gz = valid ? __ldg(P.gzsig + s) : 0.f;
+      for (int st = 0; st < N_STEPS; ++st, ++it) {
+        // ReLU' bits of this thread's 128 columns (4 words), fetched while the MMAs run
+        uint4 mw = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (st >= 1) {
+          const int ml = 8 - st;
+          mw = valid ? __ldg(reinterpret_cast<const uint4*>(P.bits + ((int64_t)ml * P.total + s) * 8 + half * 4))
+                     : make_uint4(0u, 0u, 0u, 0u);
+        }
+        const uint32_t mword[4] = {mw.x, mw.y, mw.z, mw.w};
+        mbar_wait(bar(BAR_ACC_FULL + tl), it & 1);
+        tc_fence_after();
+        float* __restrict__ db = P.db[st];
+        uint32_t buf[2][32];
+        tmem_ld32_issue(tmem_row + half * 128, buf[0]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cb = half * 4 + i;
+          uint32_t(&raw)[32] = buf[i & 1];
+          tmem_ld_wait(raw);
+          if (i + 1 < 4) tmem_ld32_issue(tmem_row + (cb + 1) * 32, buf[(i + 1) & 1]);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (st == 1) {  // + g_zsigma (x) w_sigma : the sigma head's path into h7 (nerf.py:114)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 w4 = lds128(wsig_s + (cb * 32 + 4 * j) * 4);
+              v[4 * j + 0] = fmaf(gz, w4.x, v[4 * j + 0]);
+              v[4 * j + 1] = fmaf(gz, w4.y, v[4 * j + 1]);
+              v[4 * j + 2] = fmaf(gz, w4.z, v[4 * j + 2]);
+              v[4 * j + 3] = fmaf(gz, w4.w, v[4 * j + 3]);
+            }
+          }
+          const uint32_t m32 = mword[i];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((m32 >> j) & 1u) ? v[j] : 0.f;
+          // next operand, in place (K-chunk cb/2, 16-byte chunks (cb%2)*4 .. +3)
+          const uint32_t dst = act + (cb >> 1) * CHUNK_A_BYTES + row_off;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            st_shared_v4(dst + (x4 ^ (uint32_t)(((cb & 1) * 4 + qd) << 4)), pack_bf16(v[8 * qd], v[8 * qd + 1]),
+                         pack_bf16(v[8 * qd + 2], v[8 * qd + 3]), pack_bf16(v[8 * qd + 4], v[8 * qd + 5]),
+                         pack_bf16(v[8 * qd + 6], v[8 * qd + 7]));
+          // bias gradient: column sums over this warp's 32 rows (recursive halving), one atomic per column
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int j = 0; j < o; ++j) {
+              const float send = up ? v[j] : v[j + o];
+              const float keep = up ? v[j + o] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          atomicAdd(db + cb * 32 + lane, v[0]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar(BAR_ACT_READY + tl));
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- transposed weight pack: [256 (n = input column of the layer)][64 (k = output row)] bf16 chunks, SW128 ------------
+struct PackBwdArgs {
+  int w_off[NT_N_LAYERS];
+  int in_f[NT_N_LAYERS];
+};
+
+__global__ void pack_bwd_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed, PackBwdArgs a) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
+  if (gid >= PACKED_BWD_BYTES / 16) return;
+  int byte = gid * 16, st = 0;
+  for (st = 0; st < N_STEPS; ++st) {
+    const int sb = step_chunks(st) * W_STAGE_BYTES;
+    if (byte < sb) break;
+    byte -= sb;
+  }
+  const int kc = byte / W_STAGE_BYTES;
+  byte -= kc * W_STAGE_BYTES;
+  const int n = byte / 128;
+  const int j = ((byte % 128) / 16) ^ (n & 7);
+  uint32_t out[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = kc * 64 + j * 8 + e * 2 + h;  // output row of the forward layer
+      if (st == 0)
+        v[h] = params[a.w_off[L_DIR] + k * 280 + 24 + n];       // (W_d[:, 24:])^T, k < 128
+      else if (st == 1)
+        v[h] = params[a.w_off[L_INFO] + k * 256 + n];
+      else {
+        const int i = 9 - st;                                     // trunk layer 7 .. 1
+        v[h] = params[a.w_off[i] + (int64_t)k * a.in_f[i] + n];   // first 256 input columns (hidden part of the skip)
+      }
+    }
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[0], v[1]);
+    out[e] = *reinterpret_cast<uint32_t*>(&b);
+  }
+  *reinterpret_cast<uint4*>(packed + (size_t)gid * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+}  // namespace
+
+size_t nt_bwd_tc_packed_bytes() { return PACKED_BWD_BYTES; }
+
+int nt_bwd_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t st) {
+  const LayerTable T = nt_layers();
+  PackBwdArgs a;
+  for (int i = 0; i < NT_N_LAYERS; ++i) {
+    a.w_off[i] = (int)T.w[i];
+    a.in_f[i] = kLayerIn[i];
+  }
+  const int threads = PACKED_BWD_BYTES / 16;
+  pack_bwd_kernel<<<(threads + 255) / 256, 256, 0, st>>>(params, (uint8_t*)packed, a);
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
+
+// g_u bf16 [S][128] -> outs[0] = g_info, outs[1..8] = g_7 .. g_0 (bf16 [S][256] each); db[k] accumulates colsum(outs[k])
+int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9], const void* packed, const uint32_t* bits,
+                    const float* gzsig, const float* wsig, float* const db[9], cudaStream_t st) {
+  if (S <= 0) return NT_OK;
+  static bool set = false;
+  if (!set) {
+    NT_CUDA(cudaFuncSetAttribute(bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    set = true;
+  }
+  BwdParams P;
+  memset(&P, 0, sizeof(P));
+  int rc = nt_make_map_bf16(&P.map_gu, g_u, S, 128, 128, 64, TILE_M);
+  if (rc != NT_OK) return rc;
+  for (int i = 0; i < N_STEPS; ++i) {
+    rc = nt_make_map_bf16(&P.map_out[i], outs[i], S, 256, 256, 64, TILE_M);
+    if (rc != NT_OK) return rc;
+    P.db[i] = db[i];
+  }
+  P.packed = (const uint8_t*)packed;
+  P.bits = bits;
+  P.gzsig = gzsig;
+  P.wsig = wsig;
+  P.total = S;
+  const int64_t tiles = (S + TILE_M - 1) / TILE_M;
+  P.num_pairs = (int)((tiles + 1) / 2);
+  const int grid = ctx->sm_count < P.num_pairs ? ctx->sm_count : P.num_pairs;
+  bwd_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}

@@ -154,6 +154,7 @@ struct TcStash {
   void* enc;        // bf16 [S][64]
   void* denc;       // bf16 [S][32]
   float* zsig;      // fp32 [S]
+  uint32_t* bits;   // ReLU' bit masks of the trunk layers [8][S][8]
 };
 int nt_mlp_tc_forward_stash(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                             const float* params, const void* packed, float* rgb, float* sigma, const TcStash* stash,
@@ -173,3 +174,8 @@ int nt_dw_group_begin(int S);
 int nt_dw_group_add(const void* G, int ldg, int m_valid, const void* H, int ldh, int n_valid, float* C, int ldc);
 int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st);
 int nt_make_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);
+// bwd_tc.cu — fused backward-data chain
+size_t nt_bwd_tc_packed_bytes();
+int nt_bwd_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t st);
+int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9], const void* packed, const uint32_t* bits,
+                    const float* gzsig, const float* wsig, float* const db[9], cudaStream_t st);

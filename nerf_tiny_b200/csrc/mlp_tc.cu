@@ -86,6 +86,7 @@ struct TcParams {
   // not by the epilogue threads.  maps 0..8 = st[0..8] ([S][256]), 9 = st_enc, 10 = st_denc ([S][64]).
   CUtensorMap st_map[11];
   int use_tma_stash;
+  uint32_t* st_bits;  // ReLU' bit masks of the 8 trunk layers, [8][S][8 words]: bit j of word cb = column cb*32+j > 0
 };
 
 __constant__ uint32_t c_tc_freq_point[10] = NT_FREQ_POINT_INIT;
@@ -289,6 +290,14 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
       v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4[j].y;
       v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4[j].z;
       v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4[j].w;
+    }
+    if (STASH && (KIND == EPI_RELU || KIND == EPI_RELU_SIGMA)) {
+      if (valid) {  // 1 bit per activation is all the backward-data kernel needs of this layer
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+        P.st_bits[((int64_t)L * P.total + s) * 8 + cb] = bits;
+      }
     }
     if (DBG) {
       if (P.dbg_layer == L && valid) {
@@ -1535,6 +1544,7 @@ static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const fl
     rc = nt_make_map_bf16(&P.st_map[10], stash->denc, S, 64, 64, 64, TILE_M);
     if (rc != NT_OK) return rc;
     P.use_tma_stash = getenv("NT_NO_TMA_STASH") ? 0 : 1;
+    P.st_bits = stash->bits;
   }
   P.t = t;
   P.rays = rays;

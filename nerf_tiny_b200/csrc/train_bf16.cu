@@ -19,6 +19,7 @@ struct Ws {
   float* rgb;
   bf16 *GI, *GS[8], *Gu, *Gz, *Gzs, *WT;  // GI = d point_info, GS[i] = d pre-activation of trunk layer i
   float *gzsig, *genc;
+  void* WB;  // transposed weights in the fused backward-data kernel's chunk format
   size_t bytes;
 };
 
@@ -53,6 +54,8 @@ Ws carve(void* base, int64_t S) {
   w.gzsig = (float*)take(S * 4);
   w.genc = (float*)take(S * 64 * 4);
   w.WT = (bf16*)take((size_t)WT_ELEMS * 2);
+  w.WB = take(nt_bwd_tc_packed_bytes());
+  w.st.bits = (uint32_t*)take((size_t)S * 8 * 8 * 4);
   w.bytes = off;
   return w;
 }
@@ -286,12 +289,17 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
   NT_TRY(dW(w.Gu, 128, 128, DENC, 64, 24, G + T.w[L_DIR], 280));
   NT_TRY(dW(w.Gu, 128, 128, H[8], 256, 256, G + T.w[L_DIR] + 24, 280));
   NT_TRY(colsum_bf16(ctx, w.Gu, S, 128, 128, G + T.b[L_DIR], st));
-  NT_TRY(dX(w.Gu, 128, 128, w.WT + WT_DIRINFO, 256, w.GI, nullptr, nullptr, nullptr, G + T.b[L_INFO]));  // g_info
-  // point_info (256 -> 256, linear) and the sigma head (256 -> 1, abs)
+  // fused backward-data chain: g_u -> g_info -> g_7 .. g_0 in one tcgen05 kernel (bwd_tc.cu); also the bias gradients
+  {
+    NT_TRY(nt_bwd_tc_pack(ctx, P, w.WB, st));
+    void* outs[9] = {w.GI, w.GS[7], w.GS[6], w.GS[5], w.GS[4], w.GS[3], w.GS[2], w.GS[1], w.GS[0]};
+    float* dbs[9] = {G + T.b[L_INFO], G + T.b[L_P7], G + T.b[L_P6], G + T.b[L_P5], G + T.b[L_P4],
+                     G + T.b[L_P3],   G + T.b[L_P2], G + T.b[L_P1], G + T.b[L_P0]};
+    NT_TRY(nt_bwd_tc_chain(ctx, S, w.Gu, outs, w.WB, w.st.bits, w.gzsig, P + T.w[L_SIGMA], dbs, st));
+  }
+  // weight gradients (queued): point_info, sigma head, trunk
   NT_TRY(dW(w.GI, 256, 256, H[7], 256, 256, G + T.w[L_INFO], 256));
   NT_TRY(dW(w.Gzs, 8, 1, H[7], 256, 256, G + T.w[L_SIGMA], 256));
-  // g_pre7 = relu'(h7) * (g_info . W_p + g_zsig (x) w_sigma)
-  NT_TRY(dX(w.GI, 256, 256, w.WT + WT_INFO, 256, w.GS[7], H[7], w.gzsig, P + T.w[L_SIGMA], G + T.b[L_P7]));
   for (int i = 7; i >= 1; --i) {
     bf16* cur = w.GS[i];
     NT_TRY(dW(cur, 256, 256, H[i - 1], 256, 256, G + T.w[i], kLayerIn[i]));
@@ -305,7 +313,6 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
         NT_TRY(nt_launch_gemm_tc(ctx, 0, S, 64, 256, cur, 256, w.WT + WT_ENC4, 256, e, st));
       }
     }
-    NT_TRY(dX(cur, 256, 256, w.WT + WT_TRUNK + (i - 1) * 65536, 256, w.GS[i - 1], H[i - 1], nullptr, nullptr, G + T.b[i - 1]));
   }
   NT_TRY(dW(w.GS[0], 256, 256, ENC, 64, 60, G + T.w[L_P0], 60));
   if (g_t) {
