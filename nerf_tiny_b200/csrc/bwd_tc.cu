@@ -44,7 +44,7 @@ struct BwdParams {
   CUtensorMap map_gu;             // load:  g_u  [S][128]
   CUtensorMap map_out[N_STEPS];   // store: g_info, g_7 .. g_0  [S][256]
   const uint8_t* packed;          // transposed bf16 weights in consumption order
-  const uint32_t* bits;           // ReLU' bit masks [8][S][8] (layer, sample, 256 bits)
+  const uint32_t* bits;           // ReLU' bit masks [8][S][8] (layer, sample, 256 bits; column cb*32+j = bit 31-j of word cb)
   const float* gzsig;             // [S]
   const float* wsig;              // [256] fp32 (flat parameter buffer)
   float* db[N_STEPS];             // bias gradients: point_info, layer 7 .. layer 0
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
           }
           const uint32_t m32 = mword[i];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ((m32 >> j) & 1u) ? v[j] : 0.f;
+          for (int j = 0; j < 32; ++j) v[j] = ((int)(m32 << j) < 0) ? v[j] : 0.f;  // element j sits at bit 31-j
           // next operand, in place (K-chunk cb/2, 16-byte chunks (cb%2)*4 .. +3)
           const uint32_t dst = act + (cb >> 1) * CHUNK_A_BYTES + row_off;
 #pragma unroll

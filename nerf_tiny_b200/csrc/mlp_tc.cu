@@ -271,6 +271,7 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
   constexpr int NCB = KIND == EPI_COLOUR ? 2 : 4;  // 32-column blocks per half
   const int cb0 = half * NCB;
   float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  uint32_t mbits[4] = {0u, 0u, 0u, 0u};
   uint32_t buf[2][32];  // double-buffered accumulator blocks: the next TMEM load is in flight during the math
   tmem_ld32_issue(tmem_row + cb0 * 32, buf[0]);
 #pragma unroll
@@ -292,12 +293,12 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
       v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4[j].w;
     }
     if (STASH && (KIND == EPI_RELU || KIND == EPI_RELU_SIGMA)) {
-      if (valid) {  // 1 bit per activation is all the backward-data kernel needs of this layer
-        uint32_t bits = 0;
+      // 1 bit per activation is all the backward-data kernel needs of this layer: funnel-shift the 32 sign bits of the
+      // pre-activations into one word (one SHF each); element j ends up at bit 31-j, set = ReLU passes
+      uint32_t sgn = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-        P.st_bits[((int64_t)L * P.total + s) * 8 + cb] = bits;
-      }
+      for (int j = 0; j < 32; ++j) sgn = __funnelshift_l(__float_as_uint(v[j]), sgn, 1);
+      mbits[i] = ~sgn;
     }
     if (DBG) {
       if (P.dbg_layer == L && valid) {
@@ -349,6 +350,8 @@ __device__ __forceinline__ void epilogue_layer(const TcParams& P, int L, int hal
       }
     }
   }
+  if (STASH && (KIND == EPI_RELU || KIND == EPI_RELU_SIGMA) && valid)
+    *reinterpret_cast<uint4*>(P.st_bits + ((int64_t)L * P.total + s) * 8 + cb0) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
   // ---- heads: the two column halves of a row live in warps w and w+8 (same TMEM lanes).  The upper half parks its
   // partial sums in accumulator columns it has already drained; the lower half picks them up after a 64-thread
   // named barrier.  Nothing overwrites those columns before both halves arrive on act_ready.
