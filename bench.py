@@ -316,7 +316,9 @@ def mlp_roofline(model, dev, d_row, d_col, d_pb, d_kinv, flat, flush, iters=5):
             "gemm_f32_kernel chain (fp32 accuracy path)", "bound": "tensor", "achieved": ach, "peak": pk["tf"],
             "unit": "TFLOP/s", "frac": ach / pk["tf"], "frac_of_sustained": ach / pk["tf_sustained"] if pk["tf_sustained"] else None,
             "peak_source": pk["src"] + " bf16 burst", "launch_ms": dur * 1e3, "algorithmic_flop_per_launch": flops,
-            "traffic": None}
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture summarised in
+            # profiles/r1b_mlp_tc_v3_summary.txt (113.6 MB + 273.6 MB); algorithmic bytes = 4 B t + 16 B rgb/sigma per sample
+            "traffic": 387.3e6 if prec == 2 else None, "traffic_unit": "B per launch (ncu, profiles/r1b_mlp_tc_v3_summary.txt)"}
 
 
 def bench_train(model, dev, rows17, world, rank, barrier, args):
