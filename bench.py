@@ -331,6 +331,8 @@ def bench_train(model, dev, rows17, world, rank, barrier, args):
     saved = model.network.flat_params().clone()
     model.train()
     allreduce = (lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)) if world > 1 else None
+    # N>1: the SUM all-reduce is fused into the Adam kernel over NVLink peer memory (falls back to NCCL if unavailable)
+    fused_ar = opt.enable_peer_allreduce() if world > 1 else False
     steps, warm = max(2, min(args.steps, 5)), 2
     pinned = [tuple(x.pin_memory() for x in b) for b in batches]
 
@@ -362,6 +364,8 @@ def bench_train(model, dev, rows17, world, rank, barrier, args):
             "note": "fused tcgen05 forward with bf16 activation stash + layer-major tcgen05 backward (dX / split-K dW GEMMs) "
                     "+ fused Adam; host batches, H2D inside the timed region; one SUM all-reduce of the 2.4 MB gradient "
                     "per step when N>1",
+            "grad_exchange": ("fused all-reduce+Adam kernel over NVLink peer memory" if fused_ar else
+                              ("NCCL all-reduce" if world > 1 else "none")),
             "frac_of_tc_peak": v / world * FLOP_PER_RAY_TRAIN / (peaks()["tf"] * 1e12), "last_loss": float(loss)}
 
 

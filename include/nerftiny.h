@@ -179,6 +179,16 @@ int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const float* near_
 int nt_adam_step(nt_ctx* ctx, int64_t count, float* params, const float* grads, float* m, float* v, float lr,
                  float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream);
 
+/* Fused gradient all-reduce + Adam over NVLink peer memory (multi-GPU replacement of "NCCL all-reduce, then
+ * nt_adam_step"): rank_grads is a HOST array of n_ranks device pointers — this rank's flat gradient and the peer-mapped
+ * (symmetric-memory) gradients of the other ranks, in RANK ORDER on every rank.  One kernel reads them over
+ * NVLink, sums in rank order (bit-identical parameters on all ranks) and applies the update of nt_adam_step.
+ * grad_sum_out dev [count] or NULL receives the summed gradient.  The caller provides the cross-rank barriers: all
+ * ranks' gradients complete before the call, all ranks' calls complete before any gradient buffer is rewritten. */
+int nt_adam_step_allreduce(nt_ctx* ctx, int64_t count, float* params, const float* const* rank_grads, int n_ranks,
+                           float* m, float* v, float lr, float beta1, float beta2, float eps, int64_t step,
+                           float grad_scale, float* grad_sum_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,7 @@ SIGNATURES = {
     "nt_render_workspace_bytes": (sz, [vp, i32, i64, i32]),
     "nt_render_forward": (i32, [vp, i32, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, sz, i32, vp]),
     "nt_render_backward": (i32, [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "nt_adam_step_allreduce": (i32, [vp, i64, vp, C.POINTER(vp), i32, vp, vp, f32, f32, f32, f32, i64, f32, vp, vp]),
     "nt_adam_step": (i32, [vp, i64, vp, vp, vp, vp, f32, f32, f32, f32, i64, f32, vp]),
 }
 

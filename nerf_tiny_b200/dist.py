@@ -79,3 +79,37 @@ def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad, group=group)
     return torch.cat(out, dim=0)[:n_total]
+
+
+class PeerGradExchange:
+    """Gradient exchange over NVLink peer memory instead of an NCCL all-reduce.
+
+    Every rank's flat gradient lives in a symmetric (peer-mapped) buffer.  After backward, `nt_adam_step_allreduce`
+    reads all ranks' buffers directly (NVLink 5 / NVSwitch loads), sums them in rank order and applies Adam in ONE
+    kernel; two device-side barriers bracket it.  Falls back to None (caller uses NCCL) when symmetric memory cannot be
+    set up (single process, no P2P)."""
+
+    def __init__(self, n_params: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.buf = symm_mem.empty(n_params, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.world = self.hdl.world_size
+        self.rank = self.hdl.rank
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]       # peer-mapped base pointers, rank order
+
+    @staticmethod
+    def create(n_params: int, device: torch.device, group=None):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2 or device.type != "cuda":
+            return None
+        try:
+            return PeerGradExchange(n_params, device, group)
+        except Exception as e:       # pragma: no cover  (no P2P / unsupported build)
+            import warnings
+            warnings.warn(f"symmetric memory unavailable ({e}); using the NCCL all-reduce")
+            return None
+
+    def barrier(self):
+        """Device-side cross-rank barrier on the current stream."""
+        self.hdl.barrier(channel=0)

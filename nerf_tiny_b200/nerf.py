@@ -125,6 +125,17 @@ class Network(nn.Module):
             self._flatten()
         return self._flat
 
+    def use_grad_buffer(self, buf):
+        """Make `buf` (flat fp32 [593924], e.g. a symmetric / peer-mapped allocation) the gradient storage."""
+        assert buf.numel() == _lib.N_PARAMS and buf.dtype == torch.float32
+        buf.copy_(self._flat_grad)
+        self._flat_grad = buf
+        off = 0
+        for p in self.parameters():
+            n = p.numel()
+            p.grad = buf[off:off + n].view(p.shape)
+            off += n
+
     def flat_grads(self):
         """Gather .grad into the flat buffer (no copy when the grads are already its views)."""
         off = 0
@@ -384,6 +395,20 @@ class FusedAdam(torch.optim.Optimizer):
         self.step_count = 0
         self.m = None
         self.v = None
+        self.peer = None          # dist.PeerGradExchange: fused all-reduce + Adam over NVLink peer memory
+
+    def enable_peer_allreduce(self, group=None):
+        """Multi-GPU: keep the flat gradient in symmetric memory and fuse the SUM all-reduce into the Adam kernel
+        (nt_adam_step_allreduce).  Returns False (NCCL path stays) if symmetric memory is unavailable."""
+        from . import dist as D
+        self.model._ensure_ctx()
+        net = self.model.network
+        peer = D.PeerGradExchange.create(_lib.N_PARAMS, net.flat_params().device, group)
+        if peer is None:
+            return False
+        net.use_grad_buffer(peer.buf)
+        self.peer = peer
+        return True
 
     def zero_grad(self, set_to_none=False):
         net = self.model.network
@@ -400,6 +425,17 @@ class FusedAdam(torch.optim.Optimizer):
             self.v = torch.zeros_like(flat)
         self.step_count += 1
         g = self.param_groups[0]
+        if self.peer is not None:
+            # every rank's gradient is complete -> one kernel sums all ranks' buffers over NVLink and updates -> nobody
+            # rewrites its gradient before all ranks have read it
+            peer = self.peer
+            arr = (C.c_void_p * peer.world)(*peer.ptrs)
+            peer.barrier()
+            _lib.check(model._lib.nt_adam_step_allreduce(model._ctx, flat.numel(), _ptr(flat), arr, peer.world, _ptr(self.m),
+                                                         _ptr(self.v), float(g["lr"]), g["betas"][0], g["betas"][1], g["eps"],
+                                                         self.step_count, 1.0, None, _stream()))
+            peer.barrier()
+            return
         _lib.check(model._lib.nt_adam_step(model._ctx, flat.numel(), _ptr(flat), _ptr(grad), _ptr(self.m), _ptr(self.v),
                                            float(g["lr"]), g["betas"][0], g["betas"][1], g["eps"], self.step_count, 1.0,
                                            _stream()))
@@ -439,9 +475,9 @@ def train_step(model: NeRFModel, optimizer: FusedAdam, row, column, pix_val, pos
     _lib.check(L.nt_ray_loss(model._ctx, n, _ptr(cc), _ptr(cf), _ptr(ct), _ptr(loss), _ptr(g_cc), _ptr(g_cf), _stream()))
     _lib.check(L.nt_render_backward(model._ctx, model._prec_train, n, _ptr(near), _ptr(far), _ptr(flat), _ptr(model._packed),
                                     None, _ptr(g_cc), _ptr(g_cf), _ptr(grads), _ptr(ws), ws.numel(), _stream()))
-    if grad_allreduce is not None:
-        grad_allreduce(grads)
-    optimizer.step()                                                  # nerf.py:474
+    if grad_allreduce is not None and getattr(optimizer, "peer", None) is None:
+        grad_allreduce(grads)                                         # NCCL SUM all-reduce of the flat gradient
+    optimizer.step()                                                  # nerf.py:474 (fused with the all-reduce if peer)
     return loss, cc, cf
 
 

@@ -588,3 +588,30 @@ def test_mlp_bf16_schedule_variants(ctx, dev, golden_dir, version):
         ctx.set_option(2, 0)
     assert float((r32 - r16).abs().max()) <= 1e-2
     assert float((s32 - s16).abs().max()) <= 3e-2 * max(1.0, float(s32.abs().max()))
+
+
+def test_adam_allreduce_emulated_ranks(ctx, dev):
+    """nt_adam_step_allreduce with the ranks emulated as separate local buffers (B200_PROFILING.md: with fewer GPUs than
+    ranks, run all ranks' data through one kernel): == sum in rank order, then nt_adam_step."""
+    import ctypes as C
+    from nerf_tiny_b200 import _lib
+    gen = torch.Generator().manual_seed(9)
+    n = 593924
+    p0 = torch.randn(n, generator=gen).to(dev)
+    grads = [torch.randn(n, generator=gen).to(dev) * 10.0 ** (r - 2) for r in range(4)]
+    gsum = grads[0].clone()
+    for g in grads[1:]:
+        gsum += g
+    pa, ma, va = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    pb, mb, vb = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    out = torch.empty_like(p0)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    arr = (C.c_void_p * 4)(*[g.data_ptr() for g in grads])
+    for step in (1, 2, 3):
+        ctx.adam_step(pa, gsum, ma, va, 3e-4, step)
+        _lib.check(ctx.lib.nt_adam_step_allreduce(ctx.h, n, C.c_void_p(pb.data_ptr()), arr, 4, C.c_void_p(mb.data_ptr()),
+                                                  C.c_void_p(vb.data_ptr()), 3e-4, 0.9, 0.999, 1e-7, step, 1.0,
+                                                  C.c_void_p(out.data_ptr()), st))
+    torch.cuda.synchronize()
+    assert torch.equal(out, gsum)
+    assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)

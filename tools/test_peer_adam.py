@@ -1,0 +1,52 @@
+"""2+ GPU check (run under torchrun): fused NVLink peer all-reduce + Adam == NCCL all-reduce + Adam, and all ranks stay
+bit-identical.  Prints PASS/FAIL per rank 0.  Also times both variants of the training step."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from nerf_tiny_b200 import nerf, synth
+from oracle import nerf_oracle as O
+
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+rows17 = synth.pose_rows(8, 400, 400, synth.focal_of(400))
+kinv = synth.k_inv_of(400, 400, synth.focal_of(400))
+batches = [synth.random_batch(rows17, 1024, 400, 400, torch.Generator().manual_seed(100 * s + rank)) for s in range(6)]
+
+
+def run(use_peer):
+    m = nerf.NeRFModel(64, 128, batch_ray=1024, precision="bf16")
+    m.load_state_dict(O.init_state_dict(624))
+    m = m.to(dev)
+    m.train()
+    m.check_range = False
+    opt = nerf.FusedAdam(m, lr=3e-4)
+    ok = opt.enable_peer_allreduce() if use_peer else False
+    ar = lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)
+    times = []
+    for i, b in enumerate(batches * 3):
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        nerf.train_step(m, opt, b[0], b[1], b[2], b[3], kinv, grad_allreduce=ar)
+        e1.record(); torch.cuda.synchronize()
+        if i >= 6:
+            times.append(e0.elapsed_time(e1))
+    return m.network.flat_params().clone(), ok, sum(times) / len(times)
+
+
+p_nccl, _, t_nccl = run(False)
+p_peer, ok, t_peer = run(True)
+# all ranks identical?
+ref = p_peer.clone()
+dist.broadcast(ref, src=0)
+same_across = bool(torch.equal(ref, p_peer))
+rel = float((p_peer - p_nccl).norm() / p_nccl.norm())
+flags = torch.tensor([1.0 if (ok and same_across and rel < 5e-3) else 0.0], device=dev)
+dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"peer_enabled={ok} ranks_identical={same_across} rel(peer vs nccl)={rel:.2e}  step ms: nccl {t_nccl:.3f}  peer {t_peer:.3f}")
+    print("PASS" if flags.item() == 1.0 else "FAIL")
+dist.destroy_process_group()
