@@ -229,6 +229,19 @@ class NeRFModel(nn.Module):
         except Exception:
             pass
 
+    def __getstate__(self):
+        """torch.save(model) as the reference does (nerf.py:491): drop the library handle, context and scratch."""
+        st = dict(self.__dict__)
+        for k in ("_lib", "_ctx", "_ctx_dev", "_packed", "_ws_cache"):
+            st.pop(k, None)
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._lib = _lib.load()
+        self._ctx, self._packed, self._ws_cache = None, None, {}
+        self.network._flatten()
+
     @property
     def _prec(self):
         return PRECISION[self.precision]
@@ -482,9 +495,9 @@ def train_step(model: NeRFModel, optimizer: FusedAdam, row, column, pix_val, pos
 
 
 # ----------------------------------------------------------------------------------------------------
-# NeRFRunner (nerf.py:353-530): constructor signature and trainer/display call surface.  The dataset /
-# TensorBoard / image-writing shell around the hot path is out of scope this round (SURVEY.md §8(f) rows
-# f1-f3): a runner is built from any object exposing the loader's batch tuples.
+# NeRFRunner (nerf.py:353-530): constructor signature, trainer(mode) / display() call surface, resume-from-checkpoint
+# and periodic save.  Batches come from loader.GpuRayBatches (pixels and pose rows
+# resident in HBM) when an image folder is given, or from any iterable of loader-shaped tuples.
 # ----------------------------------------------------------------------------------------------------
 class NeRFRunner():
     def __init__(self, gpu=0, img_dir=None, results_path="./results/", ckpt_path="./checkpoint/", low_res=1,
@@ -493,6 +506,7 @@ class NeRFRunner():
                  train_batches=None, disp_batches=None, height=None, width=None, focal=None, num_pic=1,
                  precision=None):
         global device, writer
+        import glob
         if not torch.cuda.is_available():
             raise _lib.NerfTinyError("NeRFRunner needs a CUDA device: the B200 path has no CPU fallback")
         device = torch.device("cuda:" + str(gpu))
@@ -501,14 +515,45 @@ class NeRFRunner():
         self.model = NeRFModel(num_coarse=n_coarse, num_fine=n_fine, batch_ray=batch_ray, precision=precision).to(device)
         self.results_path, self.ckpt_path, self.low_res = results_path, ckpt_path, low_res
         self.total_iter, self.batch_ray, self.step, self.decay_end = total_iter, batch_ray, step, decay_end
-        self.last_iter = -1
+        # resume: newest "<ckpt_path>*_<iter>.pkl" (nerf.py:404-415); both the reference's whole-module pickles and our
+        # {"model": state_dict, "optimizer": ..., "iter": ...} dictionaries are accepted
+        last_iter, opt_state = -1, None
+        ck_list = glob.glob(ckpt_path + "*.pkl")
+        if continue_ is True and ck_list:
+            best = max(ck_list, key=lambda f: int(f.split("_")[-1][:-4]))
+            last_iter = int(best.split("_")[-1][:-4])
+            print("Last iter:", last_iter)
+            blob = torch.load(best, map_location="cpu", weights_only=False)
+            if isinstance(blob, dict) and "model" in blob:
+                self.model.load_state_dict(blob["model"])
+                opt_state = blob.get("optimizer")
+            else:
+                self.model.load_state_dict(blob.state_dict())
+            self.model = self.model.to(device)
+        else:
+            print("New running created.")
+        self.last_iter = last_iter
         if train_batches is None and img_dir is not None:
-            raise _lib.NerfTinyError("image-folder datasets (loader.NeRFDataset) are outside this round's scope; "
-                                     "pass train_batches=/disp_batches= iterables of loader-shaped tuples")
+            from . import loader
+            ds = loader.NeRFDataset(root_dir=img_dir, low_res=low_res, transform=None, type=data_type, mode="train")
+            self.train_dataset = ds
+            train_batches = loader.GpuRayBatches.from_dataset(ds, batch_ray, shuffle=True, device=device)
+            height, width, focal, num_pic = ds.height, ds.width, ds.focal, ds.pic_num
+            try:
+                self.val_dataset = loader.NeRFDataset(root_dir=img_dir, low_res=low_res, type=data_type, mode="val")
+                self.disp_dataset = loader.NeRFDataset(root_dir=img_dir, low_res=low_res, type=data_type, mode="test")
+                self.val_dataloader = loader.GpuRayBatches.from_dataset(self.val_dataset, batch_ray, shuffle=True, device=device)
+                disp_batches = loader.GpuRayBatches.from_dataset(self.disp_dataset, batch_ray, shuffle=False, device=device)
+                num_pic = self.disp_dataset.pic_num
+            except (FileNotFoundError, OSError):
+                self.val_dataloader, disp_batches = train_batches, None
         self.train_dataloader = train_batches
-        self.val_dataloader = train_batches
+        if not hasattr(self, "val_dataloader"):
+            self.val_dataloader = train_batches
         self.disp_dataloader = disp_batches
         self.optimizer = FusedAdam(self.model, lr=learning, betas=(0.9, 0.999), eps=1e-7, initial_lr=learning)
+        if opt_state is not None:
+            self.optimizer.load_state_dict(opt_state)
         lam = (lambda it: lr_gamma ** (it / decay_end) if it < decay_end else lr_gamma * learning)   # nerf.py:426
         self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, lr_lambda=lam, last_epoch=self.last_iter) \
             if sched == "EXP" else torch.optim.lr_scheduler.MultiStepLR(self.optimizer, lr_milestone, lr_gamma,
@@ -519,8 +564,18 @@ class NeRFRunner():
                                       ).to(torch.float).transpose(0, 1)                               # nerf.py:433
         self.losses = []
 
+    def save_checkpoint(self, it):
+        """nerf.py:491 wrote torch.save(self.model); we store the state_dict (reference keys) AND the Adam moments the
+        reference forgot, under the same '<ckpt_path><start_time>_<iter>.pkl' name the resume logic looks for."""
+        os.makedirs(os.path.dirname(self.ckpt_path) or ".", exist_ok=True)
+        path = self.ckpt_path + self.start_time + "_" + str(it) + ".pkl"
+        sd = {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}
+        torch.save({"model": sd, "optimizer": self.optimizer.state_dict(), "iter": it}, path)
+        return path
+
     def trainer(self, mode):
-        """nerf.py:445-499 loop body (forward, ray_loss, backward, Adam, scheduler) over the batch source."""
+        """nerf.py:445-499 loop body (forward, ray_loss, backward, Adam, scheduler) over the batch source; the loss is
+        kept on the device (no per-step host sync), a checkpoint is written every `step` iterations."""
         dataloader = getattr(self, mode + "_dataloader")
         it = self.last_iter + 1
         while it < self.total_iter:
@@ -529,6 +584,9 @@ class NeRFRunner():
                 loss, _, _ = train_step(self.model, self.optimizer, row, column, pix_val, poses_bound, self.K_inv)
                 self.scheduler.step()
                 self.losses.append(loss)
+                if ((it + 1) % self.step) == 0:
+                    print("\n[ITER]", it, " [LOSS] %.4f" % float(loss))
+                    self.save_checkpoint(it)
                 it += 1
                 n_seen += 1
                 if it >= self.total_iter:
@@ -538,12 +596,20 @@ class NeRFRunner():
         self.last_iter = it - 1
         self.model.check_status()
 
-    def display(self):
-        """nerf.py:503-530: no-grad render of every test batch, scattered into (num_pic, H, W, 3)."""
+    def display(self, save=False):
+        """nerf.py:503-530: no-grad render of every test batch, scattered into (num_pic, H, W, 3); with save=True the
+        frames are written as <results_path><start_time>/<i>.jpg (uint8 conversion on the GPU)."""
         result = torch.full((self.num_pic, self.height, self.width, 3), 1.0, device=device)
         with torch.no_grad():
             self.model.eval()
             for (row, column, pix_val, poses_bound, pic) in self.disp_dataloader:
                 _, c_fine = self.model(row, column, poses_bound, self.K_inv)
                 result[pic.to(device), row.to(device), column.to(device)] = c_fine
+        if save:
+            from PIL import Image
+            out_dir = self.results_path + self.start_time + "/"
+            os.makedirs(out_dir, exist_ok=True)
+            frames = (result.clamp(0, 1) * 255.0).to(torch.uint8).cpu().numpy()
+            for i in range(self.num_pic):
+                Image.fromarray(frames[i]).save(out_dir + str(i) + ".jpg")
         return result
