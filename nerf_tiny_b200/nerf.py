@@ -433,9 +433,11 @@ class FusedAdam(torch.optim.Optimizer):
         model._ensure_ctx()
         net = model.network
         flat, grad = net.flat_params(), net.flat_grads()
-        if self.m is None or self.m.device != flat.device:
+        if self.m is None:
             self.m = torch.zeros_like(flat)
             self.v = torch.zeros_like(flat)
+        elif self.m.device != flat.device:                     # moments restored from a checkpoint
+            self.m, self.v = self.m.to(flat.device).contiguous(), self.v.to(flat.device).contiguous()
         self.step_count += 1
         g = self.param_groups[0]
         if self.peer is not None:

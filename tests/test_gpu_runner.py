@@ -1,0 +1,79 @@
+"""Runner shell on the GPU: image folder -> GPU-resident batches -> train -> checkpoint ->
+resume -> display; whole-module pickle of the model as the reference saves it (nerf.py:491)."""
+import glob
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make_scene(root, n=2, h=16, w=16):
+    from PIL import Image
+    rng = np.random.RandomState(0)
+    for mode in ("train", "val", "test"):
+        os.makedirs(root + mode, exist_ok=True)
+        frames = []
+        for i in range(n):
+            rgba = rng.randint(0, 256, (h, w, 4), dtype=np.uint8)
+            rgba[..., 3] = 255
+            Image.fromarray(rgba, "RGBA").save(root + f"{mode}/r_{i}.png")
+            m = np.eye(4)
+            m[:3, 3] = [0.3 * i, 0.1, 4.0]
+            frames.append({"file_path": f"./{mode}/r_{i}", "transform_matrix": m.tolist()})
+        json.dump({"camera_angle_x": 0.69, "frames": frames}, open(root + f"transforms_{mode}.json", "w"))
+
+
+def test_runner_train_checkpoint_resume_display(tmp_path):
+    from nerf_tiny_b200 import nerf
+    root, ck, res = str(tmp_path) + "/scene/", str(tmp_path) + "/ck/", str(tmp_path) + "/res/"
+    os.makedirs(root)
+    _make_scene(root)
+    nerf.seed_everything(7)
+    kw = dict(gpu=0, img_dir=root, results_path=res, ckpt_path=ck, low_res=1, batch_ray=64, learning=1e-3, n_coarse=64,
+              n_fine=128, data_type="sync", step=4, decay_end=1000, sched="EXP")
+    r1 = nerf.NeRFRunner(total_iter=8, continue_=False, **kw)
+    assert r1.height == 16 and r1.num_pic == 2 and len(r1.train_dataloader) == 8
+    r1.trainer("train")
+    assert len(r1.losses) == 8 and all(np.isfinite(float(l)) for l in r1.losses)
+    files = sorted(glob.glob(ck + "*.pkl"))
+    assert [int(f.split("_")[-1][:-4]) for f in files] == [3, 7]
+    w_end = r1.model.network.flat_params().clone()
+    m_end, step_end = r1.optimizer.m.clone(), r1.optimizer.step_count
+
+    r2 = nerf.NeRFRunner(total_iter=10, continue_=True, **kw)       # resumes at iteration 8 with weights AND moments
+    assert r2.last_iter == 7 and r2.optimizer.step_count == step_end
+    assert torch.equal(r2.model.network.flat_params(), w_end)
+    assert torch.equal(r2.optimizer.m.to(w_end.device), m_end)
+    assert abs(r2.optimizer.param_groups[0]["lr"] - 1e-3 * 0.1 ** (8 / 1000)) < 1e-12
+    r2.trainer("train")
+    assert len(r2.losses) == 2 and r2.last_iter == 9
+    assert not torch.equal(r2.model.network.flat_params(), w_end)
+
+    img = r2.display(save=True)
+    assert img.shape == (2, 16, 16, 3) and bool(torch.isfinite(img).all())
+    assert len(glob.glob(res + "*/*.jpg")) == 2
+
+
+def test_model_whole_module_pickle():
+    from nerf_tiny_b200 import nerf, synth
+    dev = torch.device("cuda:0")
+    nerf.seed_everything(3)
+    model = nerf.NeRFModel(batch_ray=32).to(dev)
+    rows17 = synth.pose_rows(3, 100, 100, synth.focal_of(100))
+    row, col, _, pb, _ = synth.random_batch(rows17, 32, 100, 100, torch.Generator().manual_seed(5))
+    kinv = synth.k_inv_of(100, 100, synth.focal_of(100))
+    buf = io.BytesIO()
+    torch.save(model, buf)
+    buf.seek(0)
+    clone = torch.load(buf, map_location=dev, weights_only=False)
+    assert torch.equal(clone.network.flat_params(), model.network.flat_params())
+    assert list(clone.state_dict().keys()) == list(model.state_dict().keys())
+    with torch.no_grad():
+        a = model(row, col, pb, kinv)[1]
+        b = clone(row, col, pb, kinv)[1]
+    assert torch.equal(a, b)
