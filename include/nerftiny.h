@@ -65,7 +65,7 @@ int nt_layer_table(nt_layer_desc out[NT_N_LAYERS]);
  * the gradient path t_fine -> cdf/weights -> coarse sigma that the reference keeps (nerf.py:255-259).  The fp32
  * gradient along that path is ill-conditioned; the switch lets tests compare the well-conditioned
  * part of the gradient tightly.
- * NT_OPT_MLP_TC_VERSION (default 0 = 5): schedule of the fused bf16 encode+MLP kernel — 5 tile pair in lock-step,
+ * NT_OPT_MLP_TC_VERSION (default 0 = 7 for rendering; training always 5): schedule of the fused bf16 encode+MLP kernel — 5 tile pair in lock-step,
  * 6 staggered tiles + 2-CTA cluster weight multicast, 7 staggered tiles + tcgen05 cta_group::2. */
 #define NT_OPT_DETACH_T_FINE 1
 #define NT_OPT_MLP_TC_VERSION 2

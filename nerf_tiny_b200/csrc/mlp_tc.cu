@@ -75,6 +75,7 @@ struct TcParams {
   int dbg_layer;
   int64_t total;  // samples
   int p;          // samples per ray
+  int p_shift;    // log2(p) when p is a power of two, else -1
   int num_pairs;
   // training stash (STASH instantiation): bf16 activations kept in HBM for the layer-major backward
   __nv_bfloat16* st[N_MMA_LAYERS];  // post-activation output of every tensor-core layer, [S][256] ([S][128] for dir_info)
@@ -122,6 +123,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();  // ~2 s: never hang the GPU
   }
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -1000,11 +1002,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
 namespace v7 {
 
 constexpr int NST = 4;                                // ring stages of 16 KB (this CTA's N-half of a chunk)
-__host__ __device__ constexpr bool stationary(int L) { return layer_chunks(L) <= NST; }
+// chunk stream of a layer = the loads the producer issues, in ring order.  1- and 4-chunk layers: every chunk is loaded
+// once and used by tile A, then tile B.  5-chunk layers (skip / view concatenation): [X, Y0, Y1, Y2, Y3, X] where X is the
+// encoding chunk (K-chunk 4): tile A consumes loads 0-4 (X first, released at once), tile B loads 1-5 (X last), so four
+// slots still suffice and only X is streamed twice.
+__host__ __device__ constexpr int layer_loads(int L) { return layer_chunks(L) == 5 ? 6 : layer_chunks(L); }
+__host__ __device__ constexpr int load_chunk(int L, int li) {
+  return layer_chunks(L) == 5 ? ((li == 0 || li == 5) ? 4 : li - 1) : li;
+}
 constexpr int HALF_STAGE = W_STAGE_BYTES / 2;
 constexpr int OFF_BIAS = OFF_BAR + 256;               // 2 x 1 KB double-buffered bias rows (layer parity)
 constexpr int SMEM7_BYTES = OFF_BIAS + 2048;
-enum { B_W_FULL = 0, B_W_EMPTY = 4, B_ACC_FULL = 8, B_ACT_READY = 10, B_BIAS_FULL = 12, B_PEER_ACT = 14, B_PEER_W = 16 };
+enum { B_W_FULL = 0, B_W_EMPTY = 4, B_ACC_FULL = 8, B_ACT_READY = 10, B_BIAS_FULL = 12 };
 constexpr int EPI_THREADS = 512;
 constexpr int BAR_ID_EPI_ALL = 5;                     // named barrier over all epilogue threads (ids 1-4: row quads)
 
@@ -1034,10 +1043,51 @@ __device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint
 __host__ __device__ constexpr uint32_t umma2_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
+// shared-memory matrix descriptor (K-major, SWIZZLE_128B, SBO 1024 B) split into its constant high word and the
+// address word: advancing K by 16 bf16 (32 B) is +2 on the low word
+constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | (1u << 16); }
+__device__ __forceinline__ void umma2_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(DESC_HI)
+      : "memory");
+}
+// relaxed: the relayed facts (TMA bytes landed / operand rows written and proxy-fenced) were already acquired by the
+// relaying thread from its own CTA's barrier; a release.cluster arrive costs ~700 clk per relay (measured)
+__device__ __forceinline__ void remote_arrive_raw(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
 __device__ __forceinline__ void remote_arrive(uint32_t local_bar, uint32_t target_cta) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_bar), "r"(target_cta));
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// non-blocking poll.  The leader's barriers are completed by REMOTE arrives (the peer's relays): a thread suspended inside
+// mbarrier.try_wait is not woken by those and sleeps out the hardware time limit (~700 clk measured), so the MMA thread
+// polls with test_wait instead.
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  long long t0 = 0;
+  int spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins == 4096) t0 = clock64();
+    if (spins > 4096 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t done;
@@ -1167,8 +1217,8 @@ __device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter
   }
 }
 
-template <bool STASH>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc7_kernel(const TcParams P) {
+template <bool STASH, bool TL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc7_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1180,16 +1230,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
 
   if (threadIdx.x == 0) {
     if (sbase & 1023) __trap();
+    // the leader's "full" / "ready" barriers also count one remote arrive from the peer's MMA warp (its N-half of the
+    // chunk has landed / its half of the 256-row operand is ready), so the issuing thread waits on ONE barrier per event
+    const uint32_t relay = crank == 0 ? 1u : 0u;
     for (int s = 0; s < NST; ++s) {
-      mbar_init(bar(B_W_FULL + s), 1);
+      mbar_init(bar(B_W_FULL + s), 1 + relay);
       mbar_init(bar(B_W_EMPTY + s), 1);  // the leader's tcgen05.commit.cta_group::2, multicast to both CTAs
-      mbar_init(bar(B_PEER_W + s), 1);   // (leader only) the peer's N-half of the chunk has landed
     }
     for (int tl = 0; tl < 2; ++tl) {
       mbar_init(bar(B_ACC_FULL + tl), 1);
-      mbar_init(bar(B_ACT_READY + tl), EPI_THREADS);
+      mbar_init(bar(B_ACT_READY + tl), EPI_THREADS + relay);
       mbar_init(bar(B_BIAS_FULL + tl), 1);
-      mbar_init(bar(B_PEER_ACT + tl), 1);  // (leader only) the peer's tile operand is ready
     }
     fence_mbar_init();
   }
@@ -1201,24 +1252,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == WARP_TMA) {
-    // ===================== TMA producer: my half of every chunk, multicast to both CTAs =====================
+    // ===================== TMA producer: my N-half of every load of the layer's chunk stream =====================
     if (lane == 0) {
       uint32_t q = 0;
       for (int itp = 0; itp < iters; ++itp) {
         const uint8_t* src = P.packed;
         for (int L = 0; L < N_MMA_LAYERS; ++L) {
           const uint32_t bytes = chunk_bytes(L), hbytes = bytes / 2;
-          // 4-chunk layers: the N-half of the whole layer fits the ring -> loaded ONCE, used by tile A then tile B;
-          // the 5-chunk layers (skip / view concatenation) are streamed once per tile
-          const int passes = stationary(L) ? 1 : 2;
-          for (int tl = 0; tl < passes; ++tl) {
-            for (int kc = 0; kc < layer_chunks(L); ++kc, ++q) {
-              const uint32_t stage = q % NST;
-              mbar_wait(bar(B_W_EMPTY + stage), ((q / NST) & 1) ^ 1);
-              mbar_expect_tx(bar(B_W_FULL + stage), hbytes);
-              tma_bulk_g2s(sbase + OFF_W + stage * HALF_STAGE, src + kc * bytes + crank * hbytes, hbytes,
-                           bar(B_W_FULL + stage));
-            }
+          const int nl = layer_loads(L);
+          for (int li = 0; li < nl; ++li, ++q) {
+            const int kc = load_chunk(L, li);
+            const uint32_t stage = q % NST;
+            mbar_wait(bar(B_W_EMPTY + stage), ((q / NST) & 1) ^ 1);
+            mbar_expect_tx(bar(B_W_FULL + stage), hbytes);
+            tma_bulk_g2s(sbase + OFF_W + stage * HALF_STAGE, src + kc * bytes + crank * hbytes, hbytes,
+                         bar(B_W_FULL + stage));
           }
           src += layer_chunks(L) * bytes;
         }
@@ -1226,51 +1274,88 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
     }
   } else if (warp == WARP_MMA) {
     // ===================== MMA warp: the leader issues the pair's MMAs, the peer relays readiness ==========
-    if (lane == 0) {
+    // Everything per-layer is a compile-time constant (the layer loop is fully unrolled) and descriptors are 32-bit
+    // adds: the issuing thread shares its scheduler with four busy epilogue warps, so every instruction between the
+    // last MMA of one pass and the first MMA of the next is exposed once the ~4-deep MMA queue has drained.
+    if (lane == 0 && crank != 0) {
+      uint32_t r_act, r_wfull;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_act) : "r"(bar(B_ACT_READY)), "r"(0));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_wfull) : "r"(bar(B_W_FULL)), "r"(0));
       uint32_t q = 0, lit = 0;
       for (int itp = 0; itp < iters; ++itp) {
-        for (int L = 0; L < N_MMA_LAYERS; ++L, ++lit) {
-          const int nch = layer_chunks(L);
-          const uint32_t idesc = umma2_idesc(layer_n(L));
-          const bool stat = stationary(L);
-          const uint32_t qbase = q;
-          for (int tl = 0; tl < 2; ++tl) {
-            if (stat) q = qbase;  // tile B walks the same resident chunks
-            mbar_wait(bar(B_ACT_READY + tl), lit & 1);  // this CTA's operand written + accumulator drained
-            if (crank != 0) {
-              remote_arrive(bar(B_PEER_ACT + tl), 0);
-            } else {
-              mbar_wait(bar(B_PEER_ACT + tl), lit & 1);
-              tc_fence_after();
-              if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4)
-                reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + tl * 2] = clock64();
-            }
-            const uint32_t d_tmem = tmem_base + tl * 256;
-            for (int kc = 0; kc < nch; ++kc, ++q) {
-              const uint32_t stage = q % NST;
-              const bool first_use = !stat || tl == 0;
-              if (first_use) mbar_wait(bar(B_W_FULL + stage), (q / NST) & 1);
-              if (crank != 0) {
-                if (first_use) remote_arrive(bar(B_PEER_W + stage), 0);
-                continue;
-              }
-              if (first_use) mbar_wait(bar(B_PEER_W + stage), (q / NST) & 1);
-              tc_fence_after();
-              const uint32_t b_addr = sbase + OFF_W + stage * HALF_STAGE;
-              const bool from_enc = (L == 0) || (kc == 4);
-              const uint32_t a_addr = from_enc ? sbase + OFF_ENC + tl * CHUNK_A_BYTES
-                                               : sbase + OFF_ACT + tl * ACT_BYTES + kc * CHUNK_A_BYTES;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma2_bf16(d_tmem, umma_desc(a_addr + j * 32), umma_desc(b_addr + j * 32), idesc, (kc | j) != 0);
-              if (!stat || tl == 1) umma2_commit_mc(bar(B_W_EMPTY + stage), (uint16_t)3);  // slot free in BOTH CTAs
-            }
-            if (crank == 0) {
-              umma2_commit_mc(bar(B_ACC_FULL + tl), (uint16_t)3);     // wakes both CTAs' epilogue warps
-              if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4)
-                reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + tl * 2 + 1] = clock64();
+        for (int L = 0; L < N_MMA_LAYERS; ++L, ++lit) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int nch = layer_chunks(L);
+          const bool five = nch == 5;
+#pragma unroll
+          for (int tl = 0; tl < 2; ++tl) {
+            mbar_wait(bar(B_ACT_READY + tl), lit & 1);  // my half of the 256-row operand written, accumulator drained
+            remote_arrive_raw(r_act + 8u * tl);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              if (i >= nch || (tl == 1 && !(five && i == 4))) continue;
+              const uint32_t qq = q + i + ((five && tl == 1) ? 1 : 0), stage = qq % NST;
+              mbar_wait(bar(B_W_FULL + stage), (qq / NST) & 1);   // my N-half of the chunk has landed
+              remote_arrive_raw(r_wfull + 8u * stage);
             }
           }
+          q += layer_loads(L);
+        }
+      }
+    } else if (lane == 0) {
+      const uint32_t bar_act = bar(B_ACT_READY), bar_wf = bar(B_W_FULL), bar_we = bar(B_W_EMPTY), bar_acc = bar(B_ACC_FULL);
+      const uint32_t lo_act = desc_lo(sbase + OFF_ACT), lo_enc = desc_lo(sbase + OFF_ENC), lo_w = desc_lo(sbase + OFF_W);
+      uint32_t q = 0, lit = 0;
+      for (int itp = 0; itp < iters; ++itp) {
+        const bool stamp = TL && blockIdx.x == 0 && itp < 4;
+#pragma unroll
+        for (int L = 0; L < N_MMA_LAYERS; ++L, ++lit) {
+          const int nch = layer_chunks(L);
+          const bool five = nch == 5;
+          const uint32_t idesc = umma2_idesc(layer_n(L));
+#pragma unroll
+          for (int tl = 0; tl < 2; ++tl) {
+            // loads used by this pass: tile A = loads 0..nch-1 (all first uses), tile B = the resident chunks again and,
+            // in 5-chunk layers, the re-streamed extra chunk (load 5) last
+            const uint32_t q0 = q + ((five && tl == 1) ? 1 : 0);
+            // poll every barrier of the pass at once (independent test_waits overlap their latency); in steady state the
+            // weights have landed long ago and the 16-20 MMAs go out back to back
+            uint32_t rdy = 0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              if (i >= nch) continue;
+              const bool need = tl == 0 || (five && i == 4);
+              const uint32_t qq = q0 + i;
+              rdy |= (need ? mbar_try(bar_wf + 8u * (qq % NST), (qq / NST) & 1) : 1u) << i;
+            }
+            mbar_spin(bar_act + 8u * tl, lit & 1);  // operand written + accumulator drained in BOTH CTAs
+            tc_fence_after();
+            if (stamp) reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + tl * 2] = clock64();
+            const uint32_t d_tmem = tmem_base + tl * 256;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              if (i >= nch) continue;
+              const uint32_t qq = q0 + i, stage = qq % NST;
+              if (!((rdy >> i) & 1)) {
+                mbar_spin(bar_wf + 8u * stage, (qq / NST) & 1);
+                tc_fence_after();
+              }
+              // K-chunk of the A operand behind this load: 5-chunk layers put the extra (encoding) chunk first for tile A
+              const int kc = five ? (tl == 0 ? (i == 0 ? 4 : i - 1) : i) : i;
+              const bool from_enc = (L == 0) || (kc == 4);
+              const uint32_t a_lo = from_enc ? lo_enc + tl * (CHUNK_A_BYTES >> 4)
+                                             : lo_act + tl * (ACT_BYTES >> 4) + kc * (CHUNK_A_BYTES >> 4);
+              const uint32_t b_lo = lo_w + stage * (HALF_STAGE >> 4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma2_bf16_lo(d_tmem, a_lo + 2 * j, b_lo + 2 * j, idesc, (i | j) != 0);
+              if (tl == 1 || (five && i == 0)) umma2_commit_mc(bar_we + 8u * stage, (uint16_t)3);  // slot free in BOTH CTAs
+            }
+            umma2_commit_mc(bar_acc + 8u * tl, (uint16_t)3);     // wakes both CTAs' epilogue warps
+            if (stamp) reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + tl * 2 + 1] = clock64();
+          }
+          q += layer_loads(L);
         }
       }
     }
@@ -1299,18 +1384,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
       bool valid_t[2];
       int64_t ray_t[2];
       // ---- positional encoding of both tiles' samples: this thread = one row, feature pairs 8*quarter .. +7 ----
+      // the inputs of BOTH tiles are requested first (one exposed memory latency, not two), and the next pair's lines
+      // are pulled into L2 a whole pair ahead
+      float4 rin[2][4];
+      float tin[2];
 #pragma unroll
       for (int tl = 0; tl < 2; ++tl) {
         const int64_t s = ((int64_t)pair * 2 + tl) * TILE_M + row;
         const bool valid = pair < P.num_pairs && s < P.total;
         const int64_t sc = valid ? s : P.total - 1;
-        const int64_t ray = sc / P.p;
+        const int64_t ray = P.p_shift >= 0 ? (sc >> P.p_shift) : sc / P.p;
         s_t[tl] = s;
         valid_t[tl] = valid;
         ray_t[tl] = ray;
         const float4* rp = reinterpret_cast<const float4*>(P.rays + ray * 16);
-        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
-        const float tt = __ldg(P.t + sc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rin[tl][j] = __ldg(rp + j);
+        tin[tl] = __ldg(P.t + sc);
+      }
+      if (quarter == 0 && lane == 0) {
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl) {
+          const int64_t sn = ((int64_t)(pair + (int)gridDim.x) * 2 + tl) * TILE_M + quad * 32;
+          if (sn < P.total) {
+            prefetch_l2(P.t + sn);
+            prefetch_l2(P.rays + (P.p_shift >= 0 ? (sn >> P.p_shift) : sn / P.p) * 16);
+          }
+        }
+      }
+#pragma unroll
+      for (int tl = 0; tl < 2; ++tl) {
+        const int64_t s = s_t[tl];
+        const bool valid = valid_t[tl];
+        const float4 r0 = rin[tl][0], r1 = rin[tl][1], r2 = rin[tl][2], r3 = rin[tl][3];
+        const float tt = tin[tl];
         const float pc0 = __fmul_rn(r0.x, tt), pc1 = __fmul_rn(r0.y, tt), pc2 = __fmul_rn(r0.z, tt);
         float pos[3];
         pos[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.w, pc0), __fmul_rn(r1.x, pc1)), __fmul_rn(r1.y, pc2)), r3.x);
@@ -1354,7 +1461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
           mbar_wait(bar(B_ACC_FULL + tl), it & 1);
           tc_fence_after();
           if (tl == 0) mbar_wait(bar(B_BIAS_FULL + bb), bias_use[bb] & 1);
-          if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
+          if (TL && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
             reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 4 + tl * 2] = clock64();
           if (L == 7)
             epilogue_q<EPI_RELU_SIGMA, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
@@ -1394,7 +1501,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
             tc_fence_before();
             mbar_arrive(bar(B_ACT_READY + tl));
           }
-          if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
+          if (TL && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
             reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 5 + tl * 2] = clock64();
         }
         // both tiles are done with this layer's bias row: refill the buffer with layer L+2's (next pair's for L = 8, 9)
@@ -1560,28 +1667,36 @@ static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const fl
   P.dbg_layer = dbg_layer;
   P.total = n * p;
   P.p = p;
+  P.p_shift = -1;
+  for (int b = 0; b < 30; ++b)
+    if (p == (1 << b)) P.p_shift = b;
   const int64_t tiles = (P.total + TILE_M - 1) / TILE_M;
   P.num_pairs = (int)((tiles + 1) / 2);
   if (P.num_pairs == 0) return NT_OK;
   int grid = ctx->sm_count < P.num_pairs ? ctx->sm_count : P.num_pairs;
-  // schedule variants (NT_OPT_MLP_TC_VERSION / env NT_MLP_TC_VERSION): 5 = tile pair in lock-step (default, fastest),
-  // 6 = staggered tiles + 2-CTA weight multicast, 7 = staggered tiles + cta_group::2 MMAs with layer-stationary weights
+  // schedule variants (NT_OPT_MLP_TC_VERSION / env NT_MLP_TC_VERSION): 5 = tile pair in lock-step (the training
+  // instantiation and the per-layer debug dump always use it), 6 = staggered tiles + 2-CTA weight multicast,
+  // 7 = staggered tiles + cta_group::2 MMAs with layer-stationary weights (default for rendering, fastest)
   int ver = ctx->opt_tc_version;
   if (ver == 0) {
     const char* e = getenv("NT_MLP_TC_VERSION");
-    ver = e ? atoi(e) : 5;
+    ver = e ? atoi(e) : 7;
   }
   const bool use_v6 = ver == 6, use_v7 = ver == 7;
   if (use_v7 && (!dbg || dbg_layer >= 100) && !stash) {
     static bool set7 = false;
     if (!set7) {
-      NT_CUDA(cudaFuncSetAttribute(v7::mlp_tc7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::SMEM7_BYTES));
+      NT_CUDA(cudaFuncSetAttribute(v7::mlp_tc7_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::SMEM7_BYTES));
+      NT_CUDA(cudaFuncSetAttribute(v7::mlp_tc7_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::SMEM7_BYTES));
       set7 = true;
     }
     int g7 = ctx->sm_count & ~1;                       // whole 2-CTA clusters
     const int need = ((P.num_pairs + 1) / 2) * 2;
     if (g7 > need) g7 = need;
-    v7::mlp_tc7_kernel<false><<<g7, N_THREADS, v7::SMEM7_BYTES, st>>>(P);
+    if (dbg)
+      v7::mlp_tc7_kernel<false, true><<<g7, N_THREADS, v7::SMEM7_BYTES, st>>>(P);
+    else
+      v7::mlp_tc7_kernel<false, false><<<g7, N_THREADS, v7::SMEM7_BYTES, st>>>(P);
     NT_LAUNCH_CHECK(ctx);
     return NT_OK;
   }

@@ -17,9 +17,11 @@ for _ in range(2):
 torch.cuda.synchronize()
 prof = dbg.cpu().numpy().view(np.int64).reshape(-1)[:4 * 10 * 16].reshape(4, 10, 16)
 t0 = prof[1, 0, 0]
-names = ["mmaA_start", "mmaA_end", "mmaB_start", "mmaB_end", "epiA_wake", "epiA_done", "epiB_wake", "epiB_done"]
+names = ["mmaA_start", "mmaA_end", "mmaB_start", "mmaB_end", "epiA_wake", "epiA_done", "epiB_wake", "epiB_done",
+         "iss0", "iss1", "iss2", "iss3", "preActA", "rdy", "actA_ok", "actB_ok"]
+NS = 8 if os.environ.get("NT_MLP_TC_VERSION") == "7" else 8
 for pl in (1, 2):
     print("pair", pl)
     for L in range(10):
-        r = prof[pl, L] - t0
-        print(f" L{L}: " + "  ".join(f"{names[i]}={r[i]}" for i in range(8)))
+        r = prof[pl, L] - t0; r[13:14] = prof[pl, L, 13:14]
+        print(f" L{L}: " + "  ".join(f"{names[i]}={r[i]}" for i in range(NS)))
