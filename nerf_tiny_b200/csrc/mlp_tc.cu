@@ -210,7 +210,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 
 // sin/cos for the bf16 path: 2-term Cody-Waite reduction by 2*pi, then the SFU (abs err ~1e-6, far below bf16's 4e-3)
 __device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
-  const float k = rintf(x * 0.15915494309189535f);
+  // round-to-nearest by the 1.5 * 2^23 trick (|x / 2pi| < 2^22 here): two FADD-class ops instead of an XU-pipe FRND
+  const float k = __fadd_rn(__fmaf_rn(x, 0.15915494309189535f, 12582912.f), -12582912.f);
   float r = fmaf(k, -6.2831854820251465f, x);
   r = fmaf(k, 1.7484555314695172e-07f, r);
   s = __sinf(r);
