@@ -312,13 +312,13 @@ def mlp_roofline(model, dev, d_row, d_col, d_pb, d_kinv, flat, flush, iters=5):
     flops = FLOP_PER_SAMPLE * n * 128
     pk = peaks()
     ach = flops / dur / 1e12
-    return {"kernel": "mlp_tc_kernel (fused encode + 8x256 MLP, fine pass 128 samples/ray)" if prec == 2 else
+    return {"kernel": "mlp_tc7_kernel (fused encode + 8x256 MLP, cta_group::2 schedule, fine pass 128 samples/ray)" if prec == 2 else
             "gemm_f32_kernel chain (fp32 accuracy path)", "bound": "tensor", "achieved": ach, "peak": pk["tf"],
             "unit": "TFLOP/s", "frac": ach / pk["tf"], "frac_of_sustained": ach / pk["tf_sustained"] if pk["tf_sustained"] else None,
             "peak_source": pk["src"] + " bf16 burst", "launch_ms": dur * 1e3, "algorithmic_flop_per_launch": flops,
             # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture summarised in
-            # profiles/r1b_mlp_tc_v3_summary.txt (113.6 MB + 273.6 MB); algorithmic bytes = 4 B t + 16 B rgb/sigma per sample
-            "traffic": 387.3e6 if prec == 2 else None, "traffic_unit": "B per launch (ncu, profiles/r1b_mlp_tc_v3_summary.txt)"}
+            # profiles/r1j_mlp_tc7_summary.txt (110.8 MB + 277.2 MB); algorithmic bytes = 4 B t + 16 B rgb/sigma per sample
+            "traffic": 388.0e6 if prec == 2 else None, "traffic_unit": "B per launch (ncu, profiles/r1j_mlp_tc7_summary.txt)"}
 
 
 def bench_train(model, dev, rows17, world, rank, barrier, args):
@@ -361,7 +361,7 @@ def bench_train(model, dev, rows17, world, rank, barrier, args):
     return {"metric": "rays/sec (train step: fwd+bwd+Adam, coarse64+fine128)", "value": v, "unit": "rays/s",
             "ms_per_step": ms, "rays_per_step_per_gpu": TRAIN_BATCH, "steps": steps,
             "dtype": "bf16" if args.precision == "bf16" else "f32",
-            "note": "fused tcgen05 forward with bf16 activation stash + layer-major tcgen05 backward (dX / split-K dW GEMMs) "
+            "note": "fused tcgen05 forward with TMA-stored bf16 stash + fused tcgen05 backward-data chain + one grouped split-K dW launch per pass "
                     "+ fused Adam; host batches, H2D inside the timed region; one SUM all-reduce of the 2.4 MB gradient "
                     "per step when N>1",
             "grad_exchange": ("fused all-reduce+Adam kernel over NVLink peer memory" if fused_ar else
