@@ -236,6 +236,16 @@ enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_COLOUR = 3 };
       reinterpret_cast<long long*>(P.dbg)[(pair_local * 10 + L) * 16 + (slot)] = clock64();                  \
   } while (0)
 
+// (d0, d1) = (a0, a1) + (b0, b1) in one packed instruction (sm_100 add.f32x2; same rounding as two add.rn.f32)
+__device__ __forceinline__ void add_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 pa, pb, pd;\n\t"
+      "mov.b64 pa, {%2, %3};\n\t"
+      "mov.b64 pb, {%4, %5};\n\t"
+      "add.rn.f32x2 pd, pa, pb;\n\t"
+      "mov.b64 {%0, %1}, pd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -1137,11 +1147,9 @@ __device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter
     for (int j = 0; j < 8; ++j) b4[j] = lds128(bias_s + cb * 128 + j * 16);
     float v[32];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b4[j].x;
-      v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4[j].y;
-      v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4[j].z;
-      v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4[j].w;
+    for (int j = 0; j < 8; ++j) {  // packed fp32 adds (FADD2): half the instructions of the bias add
+      add_f32x2(v[4 * j + 0], v[4 * j + 1], __uint_as_float(raw[4 * j + 0]), __uint_as_float(raw[4 * j + 1]), b4[j].x, b4[j].y);
+      add_f32x2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]), b4[j].z, b4[j].w);
     }
     if (KIND == EPI_RELU_SIGMA) {  // sigma head (nerf.py:94, :114); weights from the fp32 side block in L1/L2
       const float4* __restrict__ ws = reinterpret_cast<const float4*>(aux_g + 7 * AUX_REC_FLOATS + AUX_EXTRA + cb * 32);

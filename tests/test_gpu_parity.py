@@ -590,6 +590,35 @@ def test_mlp_bf16_schedule_variants(ctx, dev, golden_dir, version):
     assert float((s32 - s16).abs().max()) <= 3e-2 * max(1.0, float(s32.abs().max()))
 
 
+@pytest.mark.parametrize("version", [5, 7])
+@pytest.mark.parametrize("n_rays,p", [(1, 64), (1, 128), (2, 64), (3, 128), (5, 64), (37, 64), (149, 128), (297, 100)])
+def test_mlp_bf16_small_and_ragged_launches(ctx, dev, golden_dir, version, n_rays, p):
+    """Launches smaller than one tile, one pair, one CTA pair and one wave (the cta_group::2 schedule needs whole
+    clusters and an even trip count), and a samples-per-ray count that is neither a power of two nor a divisor of the
+    128-sample tile: every schedule still matches the fp32 path, and two runs are bit-identical."""
+    g = load(golden_dir, "fern64")
+    flat = flat_of(sd_of("trained64"), dev)
+    packed = ctx.pack(flat, BF16)
+    reps = (n_rays + 63) // 64
+    row = cu(np.tile(g["row"], reps)[:n_rays], dev)
+    col = cu(np.tile(g["col"], reps)[:n_rays], dev)
+    c2w = cu(np.tile(g["c2w"], (reps, 1, 1))[:n_rays], dev)
+    rays, _, de = ctx.raygen(row, col, c2w, cu(g["k_inv"], dev))
+    tf = np.tile(g["t_fine"], (reps, 1))[:n_rays]
+    t = cu(np.ascontiguousarray(np.resize(tf, (n_rays, p)) if p > 128 else tf[:, :p]), dev)
+    r32, s32, _ = ctx.mlp_forward(FP32, t, rays, de, flat)
+    ctx.set_option(2, version)
+    try:
+        r16, s16, _ = ctx.mlp_forward(BF16, t, rays, de, flat, packed)
+        r16b, s16b, _ = ctx.mlp_forward(BF16, t, rays, de, flat, packed)
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_option(2, 0)
+    assert r16.shape == (n_rays, p, 3) and torch.equal(r16, r16b) and torch.equal(s16, s16b)
+    assert float((r32 - r16).abs().max()) <= 1e-2
+    assert float((s32 - s16).abs().max()) <= 3e-2 * max(1.0, float(s32.abs().max()))
+
+
 def test_adam_allreduce_emulated_ranks(ctx, dev):
     """nt_adam_step_allreduce with the ranks emulated as separate local buffers (B200_PROFILING.md: with fewer GPUs than
     ranks, run all ranks' data through one kernel): == sum in rank order, then nt_adam_step."""
