@@ -459,18 +459,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
                 mbar_wait(bar(BAR_ACT_READY + tl), lit & 1);
                 tc_fence_after();
                 TC_PROF(tl);
-                if (STASH && P.use_tma_stash) {
-                  // this layer's operand = the previous layer's bf16 output (or the features): stash it from smem
+                if (STASH && P.use_tma_stash && L == 0) {
+                  // layer 0's operand = the xyz features: stash them from smem
                   const int row0 = (pair * 2 + tl) * TILE_M;
                   if (row0 < P.total) {
-                    if (L == 0) {
-                      tma_store_2d(&P.st_map[9], 0, row0, sbase + OFF_ENC + tl * CHUNK_A_BYTES);
-                    } else {
-#pragma unroll
-                      for (int c = 0; c < 4; ++c)
-                        tma_store_2d(&P.st_map[L - 1], c * 64, row0, sbase + OFF_ACT + tl * ACT_BYTES + c * CHUNK_A_BYTES);
-                      if (L == 9) tma_store_2d(&P.st_map[10], 0, row0, sbase + OFF_ENC + tl * CHUNK_A_BYTES);
-                    }
+                    tma_store_2d(&P.st_map[9], 0, row0, sbase + OFF_ENC + tl * CHUNK_A_BYTES);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                   }
                 }
@@ -489,6 +482,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 4; ++j)  // 4 x (K = 16) inside the 64-wide swizzled chunk: +32 B per step
                 umma_bf16(d_tmem, umma_desc(a_addr + j * 32), umma_desc(b_addr + j * 32), idesc, (kc | j) != 0);
+              if (STASH && P.use_tma_stash && L > 0) {
+                // this K-chunk of the operand = 64 columns of the previous layer's bf16 output (chunk 4 of dir_info = the
+                // view features): stash it from smem.  One 16 KB box per chunk step, not the whole tile at once, so the
+                // weight loads of the next chunks are not queued behind 128 KB of stores in the TMA unit.
+                const int row0 = (pair * 2 + tl) * TILE_M;
+                if (row0 < P.total && (kc < 4 || L == 9)) {
+                  if (kc < 4)
+                    tma_store_2d(&P.st_map[L - 1], kc * 64, row0, a_addr);
+                  else
+                    tma_store_2d(&P.st_map[10], 0, row0, a_addr);
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+              }
               if (kc == nch - 1) {
                 // the epilogue that this commit releases overwrites the operand tiles: TMA stash reads must be done
                 if (STASH && P.use_tma_stash) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
