@@ -236,11 +236,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
                   tma_load_2d(act, &P.map_gu, 0, row0, bar(BAR_A_FULL + tl));
                   tma_load_2d(act + CHUNK_A_BYTES, &P.map_gu, 64, row0, bar(BAR_A_FULL + tl));
                   mbar_wait(bar(BAR_A_FULL + tl), pl & 1);
-                } else if (row0 < P.total) {
-                  // the operand of this step is the output of step st-1: stash it for the weight-gradient GEMM
-#pragma unroll
-                  for (int c = 0; c < 4; ++c) tma_store_2d(&P.map_out[st - 1], c * 64, row0, act + c * CHUNK_A_BYTES);
-                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
               }
               const uint32_t a_addr = act + kc * CHUNK_A_BYTES;
@@ -248,6 +243,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 umma_bf16(d_tmem, umma_desc(a_addr + j * 32), umma_desc(b_addr + j * 32), idesc, (kc | j) != 0);
+              if (st > 0) {
+                // the operand of this step is the output of step st-1: stash it for the weight-gradient GEMM, one 16 KB
+                // box per K-chunk step so the next chunks' weight loads are not queued behind 128 KB of stores
+                const int row0 = (pair * 2 + tl) * TILE_M;
+                if (row0 < P.total) {
+                  tma_store_2d(&P.map_out[st - 1], kc * 64, row0, a_addr);
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+              }
               if (kc == nch - 1) {
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // epilogue will overwrite the operand tile
                 umma_commit(bar(BAR_ACC_FULL + tl));
