@@ -137,6 +137,17 @@ __global__ void expand_dir_enc_kernel(int64_t total, int p, const float* __restr
 }
 
 // g_enc [S,ld] (60 used) -> g_t [S]  (SURVEY.md B.4): g_p_c = sum_l w_l (g_sin*cos - g_cos*sin); g_t = g_p . d_wrd
+// FAST (bf16 training path, ld = 64): the row is read as 15 float4 and sin/cos come from the SFU after the same
+// two-constant range reduction the fused forward kernel uses (abs error 5e-7, far inside the bf16 operand rounding);
+// the fp32 path keeps sincosf.
+__device__ __forceinline__ void fast_sincos_rr(float x, float& s, float& c) {
+  const float k = __fadd_rn(__fmaf_rn(x, 0.15915494309189535f, 12582912.f), -12582912.f);
+  float r = fmaf(k, -6.2831854820251465f, x);
+  r = fmaf(k, 1.7484555314695172e-07f, r);
+  s = __sinf(r);
+  c = __cosf(r);
+}
+template <bool FAST>
 __global__ void encode_backward_kernel(int64_t total, int p, const float* __restrict__ t, const float* __restrict__ rays,
                                        const float* __restrict__ g_enc, int ld, float* __restrict__ g_t) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,6 +155,18 @@ __global__ void encode_backward_kernel(int64_t total, int p, const float* __rest
   const float* ray = rays + (s / p) * 16;
   float pos[3];
   sample_position(ray, t[s], pos);
+  float gl[60];
+  if (FAST) {
+    const float4* g4 = reinterpret_cast<const float4*>(g_enc + s * ld);
+#pragma unroll
+    for (int q = 0; q < 15; ++q) {
+      const float4 v = __ldg(g4 + q);
+      gl[4 * q] = v.x; gl[4 * q + 1] = v.y; gl[4 * q + 2] = v.z; gl[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 60; ++q) gl[q] = g_enc[s * ld + q];
+  }
   float acc = 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -151,13 +174,15 @@ __global__ void encode_backward_kernel(int64_t total, int p, const float* __rest
     float dw = __fadd_rn(__fadd_rn(__fmul_rn(ray[3 + c * 3], ray[0]), __fmul_rn(ray[4 + c * 3], ray[1])),
                          __fmul_rn(ray[5 + c * 3], ray[2]));
     float gp = 0.f;
-    const float* g = g_enc + s * ld + c * 20;
 #pragma unroll
     for (int l = 0; l < 10; ++l) {
       float w = __uint_as_float(c_freq_point[l]);
       float sn, cs;
-      sincosf(__fmul_rn(w, pos[c]), &sn, &cs);
-      gp += w * (g[2 * l] * cs - g[2 * l + 1] * sn);
+      if (FAST)
+        fast_sincos_rr(__fmul_rn(w, pos[c]), sn, cs);
+      else
+        sincosf(__fmul_rn(w, pos[c]), &sn, &cs);
+      gp += w * (gl[c * 20 + 2 * l] * cs - gl[c * 20 + 2 * l + 1] * sn);
     }
     acc += gp * dw;
   }
@@ -217,7 +242,10 @@ int nt_launch_encode_backward(nt_ctx* ctx, int64_t n, int p, const float* t, con
                               int ld, float* g_t, cudaStream_t st) {
   int64_t total = n * p;
   if (total <= 0) return NT_OK;
-  encode_backward_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(total, p, t, rays, g_enc, ld, g_t);
+  if (ld == 64 && (reinterpret_cast<uintptr_t>(g_enc) & 15) == 0)   // bf16 training path: padded, 16-byte aligned rows
+    encode_backward_kernel<true><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(total, p, t, rays, g_enc, ld, g_t);
+  else
+    encode_backward_kernel<false><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(total, p, t, rays, g_enc, ld, g_t);
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;
 }

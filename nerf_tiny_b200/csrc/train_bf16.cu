@@ -88,12 +88,20 @@ __global__ void pack_transposed_kernel(const float* __restrict__ params, bf16* _
   wt[gid] = __float2bfloat16_rn(v);
 }
 
-// head activations backward (B.6) + the colour layer's input gradient, one thread per sample
-__global__ void heads_backward_kernel(int64_t S, const float* __restrict__ rgb, const float* __restrict__ zsig,
-                                      const float* __restrict__ g_rgb, const float* __restrict__ g_sigma,
-                                      const bf16* __restrict__ U, const float* __restrict__ Wc, bf16* __restrict__ Gz,
-                                      bf16* __restrict__ Gzs, float* __restrict__ gzsig, bf16* __restrict__ Gu,
-                                      float* __restrict__ db_col, float* __restrict__ db_sig) {
+// head activations backward (B.6) + the colour layer's input gradient + the dir_info bias gradient.
+// Phase 1: one thread per sample (sigmoid' / abs', fp32 bias gradients of the two heads by warp reduction).
+// Phase 2: the warp walks its 32 samples together, lane = 4 columns of the 128-wide row, so the u row is read and the
+// g_u row written as one contiguous 256 B access per sample; each lane keeps the fp32 column sums of what it produced
+// (= db of dir_info), reduced over the block's 4 warps in shared memory and added with one atomic per column per block.
+__global__ void __launch_bounds__(128) heads_backward_kernel(int64_t S, const float* __restrict__ rgb,
+                                                             const float* __restrict__ zsig, const float* __restrict__ g_rgb,
+                                                             const float* __restrict__ g_sigma, const bf16* __restrict__ U,
+                                                             const float* __restrict__ Wc, bf16* __restrict__ Gz,
+                                                             bf16* __restrict__ Gzs, float* __restrict__ gzsig,
+                                                             bf16* __restrict__ Gu, float* __restrict__ db_col,
+                                                             float* __restrict__ db_sig, float* __restrict__ db_dir) {
+  __shared__ float part[4][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = s < S;
   float gz[3] = {0.f, 0.f, 0.f};
@@ -116,44 +124,58 @@ __global__ void heads_backward_kernel(int64_t S, const float* __restrict__ rgb, 
       r2 += __shfl_xor_sync(0xffffffffu, r2, o);
       r3 += __shfl_xor_sync(0xffffffffu, r3, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
       atomicAdd(db_col + 0, r0);
       atomicAdd(db_col + 1, r1);
       atomicAdd(db_col + 2, r2);
       atomicAdd(db_sig, r3);
     }
   }
-  if (!live) return;
-  gzsig[s] = gs;
-  uint4 o;
-  o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[0])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[1])) << 16);
-  o.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[2]));
-  o.z = o.w = 0u;
-  *reinterpret_cast<uint4*>(Gz + s * 8) = o;
-  o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gs));
-  o.y = 0u;
-  *reinterpret_cast<uint4*>(Gzs + s * 8) = o;
-  // g_u = relu'(u) * (g_z . W_c)   (nerf.py:98-99)
-  const uint4* urow = reinterpret_cast<const uint4*>(U + s * 128);
-  uint4* grow = reinterpret_cast<uint4*>(Gu + s * 128);
-#pragma unroll 4
-  for (int q = 0; q < 16; ++q) {
-    const uint4 u4 = urow[q];
-    const uint32_t uw[4] = {u4.x, u4.y, u4.z, u4.w};
-    uint32_t ow[4];
-#pragma unroll
-    for (int k2 = 0; k2 < 4; ++k2) {
-      const int j = q * 8 + k2 * 2;
-      float g0 = gz[0] * __ldg(Wc + j) + gz[1] * __ldg(Wc + 128 + j) + gz[2] * __ldg(Wc + 256 + j);
-      float g1 = gz[0] * __ldg(Wc + j + 1) + gz[1] * __ldg(Wc + 128 + j + 1) + gz[2] * __ldg(Wc + 256 + j + 1);
-      const uint32_t lo = uw[k2] & 0xffffu, hi = uw[k2] >> 16;
-      if (!(lo != 0 && lo < 0x8000u)) g0 = 0.f;
-      if (!(hi != 0 && hi < 0x8000u)) g1 = 0.f;
-      ow[k2] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g0)) |
-               ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g1)) << 16);
-    }
-    grow[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  if (live) {
+    gzsig[s] = gs;
+    uint4 o;
+    o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[0])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[1])) << 16);
+    o.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[2]));
+    o.z = o.w = 0u;
+    *reinterpret_cast<uint4*>(Gz + s * 8) = o;
+    o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gs));
+    o.y = 0u;
+    *reinterpret_cast<uint4*>(Gzs + s * 8) = o;
   }
+  // g_u = relu'(u) * (g_z . W_c)   (nerf.py:98-99): this lane's 4 columns of the colour weights stay in registers
+  float wc[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wc[c][k] = __ldg(Wc + c * 128 + lane * 4 + k);  // flat parameters are only 4-byte aligned
+  }
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t s_warp = (int64_t)blockIdx.x * blockDim.x + warp * 32;
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    const float z0 = __shfl_sync(0xffffffffu, gz[0], i), z1 = __shfl_sync(0xffffffffu, gz[1], i),
+                z2 = __shfl_sync(0xffffffffu, gz[2], i);
+    const int64_t si = s_warp + i;
+    if (si >= S) break;  // uniform across the warp
+    const uint2 u2 = *reinterpret_cast<const uint2*>(U + si * 128 + lane * 4);
+    const uint32_t uh[4] = {u2.x & 0xffffu, u2.x >> 16, u2.y & 0xffffu, u2.y >> 16};
+    float g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      g[k] = z0 * wc[0][k] + z1 * wc[1][k] + z2 * wc[2][k];
+      if (!(uh[k] != 0 && uh[k] < 0x8000u)) g[k] = 0.f;  // u > 0 as a bf16 bit pattern
+      cs[k] += g[k];
+    }
+    uint2 o2;
+    o2.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g[0])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g[1])) << 16);
+    o2.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g[2])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g[3])) << 16);
+    *reinterpret_cast<uint2*>(Gu + si * 128 + lane * 4) = o2;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) part[warp][lane * 4 + k] = cs[k];
+  __syncthreads();
+  const int col = threadIdx.x;
+  atomicAdd(db_dir + col, (part[0][col] + part[1][col]) + (part[2][col] + part[3][col]));
 }
 
 // column sums of a bf16 matrix [rows][ld] accumulated (fp32 atomics) into out[cols]; cols even.
@@ -261,7 +283,7 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
   }
   heads_backward_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(S, w.rgb, w.st.zsig, g_rgb, g_sigma, H[9],
                                                                      P + T.w[L_COLOR], w.Gz, w.Gzs, w.gzsig, w.Gu,
-                                                                     G + T.b[L_COLOR], G + T.b[L_SIGMA]);
+                                                                     G + T.b[L_COLOR], G + T.b[L_SIGMA], G + T.b[L_DIR]);
   NT_LAUNCH_CHECK(ctx);
 
   // every weight gradient of this pass is queued and computed by ONE grouped tensor-core launch at the end
@@ -288,7 +310,6 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
   // dir_info on [dir_enc | point_info] (nerf.py:118)
   NT_TRY(dW(w.Gu, 128, 128, DENC, 64, 24, G + T.w[L_DIR], 280));
   NT_TRY(dW(w.Gu, 128, 128, H[8], 256, 256, G + T.w[L_DIR] + 24, 280));
-  NT_TRY(colsum_bf16(ctx, w.Gu, S, 128, 128, G + T.b[L_DIR], st));
   // fused backward-data chain: g_u -> g_info -> g_7 .. g_0 in one tcgen05 kernel (bwd_tc.cu); also the bias gradients
   {
     NT_TRY(nt_bwd_tc_pack(ctx, P, w.WB, st));
