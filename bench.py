@@ -336,9 +336,15 @@ def bench_train(model, dev, rows17, world, rank, barrier, args):
     steps, warm = max(2, min(args.steps, 5)), 2
     pinned = [tuple(x.pin_memory() for x in b) for b in batches]
 
+    # forward / loss / backward replayed from one CUDA graph (NT_TRAIN_GRAPH=0: launch by launch through train_step)
+    graphed = nerf.GraphedTrainStep(model, opt, TRAIN_BATCH, k_inv) if os.environ.get("NT_TRAIN_GRAPH", "1") != "0" else None
+
     def one(i):
         row, col, pix, pb, pic = pinned[i % len(pinned)]
-        loss, _, _ = nerf.train_step(model, opt, row, col, pix, pb, k_inv, grad_allreduce=allreduce)
+        if graphed is not None:
+            loss, _, _ = graphed(row, col, pix, pb, grad_allreduce=allreduce)
+        else:
+            loss, _, _ = nerf.train_step(model, opt, row, col, pix, pb, k_inv, grad_allreduce=allreduce)
         return loss
     for i in range(warm):
         one(i)
@@ -362,7 +368,7 @@ def bench_train(model, dev, rows17, world, rank, barrier, args):
             "ms_per_step": ms, "rays_per_step_per_gpu": TRAIN_BATCH, "steps": steps,
             "dtype": "bf16" if args.precision == "bf16" else "f32",
             "note": "fused tcgen05 forward with TMA-stored bf16 stash + fused tcgen05 backward-data chain + one grouped split-K dW launch per pass "
-                    "+ fused Adam; host batches, H2D inside the timed region; one SUM all-reduce of the 2.4 MB gradient "
+                    "+ fused Adam; forward/loss/backward replayed as one CUDA graph; host batches, H2D inside the timed region; one SUM all-reduce of the 2.4 MB gradient "
                     "per step when N>1",
             "grad_exchange": ("fused all-reduce+Adam kernel over NVLink peer memory" if fused_ar else
                               ("NCCL all-reduce" if world > 1 else "none")),

@@ -496,6 +496,66 @@ def train_step(model: NeRFModel, optimizer: FusedAdam, row, column, pix_val, pos
     return loss, cc, cf
 
 
+class GraphedTrainStep:
+    """`train_step` for a fixed batch size with the forward / loss / backward launches (~45 kernels, most of them a few
+    microseconds) captured ONCE into a CUDA graph and replayed: the inputs are copied into static device buffers, the
+    fused Adam - whose step count and learning rate change every iteration - and the multi-GPU gradient exchange stay
+    ordinary launches after the replay.  Same arithmetic, same kernels, same order as `train_step`."""
+
+    def __init__(self, model: NeRFModel, optimizer: FusedAdam, n_rays: int, K_inv):
+        dev = model._ensure_ctx()
+        self.model, self.opt, self.n = model, optimizer, int(n_rays)
+        self.row = torch.zeros(self.n, dtype=torch.int64, device=dev)
+        self.col = torch.zeros(self.n, dtype=torch.int64, device=dev)
+        self.pix = torch.zeros(self.n, 3, dtype=torch.float32, device=dev)
+        self.pb = torch.zeros(self.n, 17, dtype=torch.float32, device=dev)
+        self.kinv = _dev_f32(K_inv, dev)
+        self.graph = None
+        self.out = None
+
+    def _body(self):
+        model, L = self.model, self.model._lib
+        net = model.network
+        flat, grads = net.flat_params(), net.flat_grads()
+        near, far = self.pb[:, 15].contiguous(), self.pb[:, 16].contiguous()
+        grads.zero_()
+        cc, cf, ws = model._render_raw(flat, self.row, self.col, self.pb, self.kinv, near, far, train=True)
+        loss = torch.empty(1, dtype=torch.float32, device=flat.device)
+        g_cc, g_cf = torch.empty_like(cc), torch.empty_like(cf)
+        _lib.check(L.nt_ray_loss(model._ctx, self.n, _ptr(cc), _ptr(cf), _ptr(self.pix), _ptr(loss), _ptr(g_cc), _ptr(g_cf),
+                                 _stream()))
+        _lib.check(L.nt_render_backward(model._ctx, model._prec_train, self.n, _ptr(near), _ptr(far), _ptr(flat),
+                                        _ptr(model._packed), None, _ptr(g_cc), _ptr(g_cf), _ptr(grads), _ptr(ws),
+                                        ws.numel(), _stream()))
+        return loss, cc, cf, (near, far, ws, g_cc, g_cf)
+
+    def _capture(self):
+        side = torch.cuda.Stream(device=self.row.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # eager warm-up: one-time attribute / table setup inside the library
+            self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._body()
+
+    def __call__(self, row, column, pix_val, poses_bound, grad_allreduce=None):
+        if row.shape[0] != self.n:
+            raise _lib.NerfTinyError("GraphedTrainStep was built for %d rays, got %d" % (self.n, row.shape[0]))
+        self.row.copy_(row, non_blocking=True)
+        self.col.copy_(column, non_blocking=True)
+        self.pix.copy_(pix_val, non_blocking=True)
+        self.pb.copy_(poses_bound, non_blocking=True)      # float64 loader rows are converted by the copy (nerf.py:338)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        if grad_allreduce is not None and getattr(self.opt, "peer", None) is None:
+            grad_allreduce(self.model.network.flat_grads())
+        self.opt.step()
+        return self.out[0], self.out[1], self.out[2]
+
+
 # ----------------------------------------------------------------------------------------------------
 # NeRFRunner (nerf.py:353-530): constructor signature, trainer(mode) / display() call surface, resume-from-checkpoint
 # and periodic save (SURVEY.md §8(f) rows f1-f3).  Batches come from loader.GpuRayBatches (pixels and pose rows
@@ -583,7 +643,13 @@ class NeRFRunner():
         while it < self.total_iter:
             n_seen = 0
             for (row, column, pix_val, poses_bound, pic) in dataloader:
-                loss, _, _ = train_step(self.model, self.optimizer, row, column, pix_val, poses_bound, self.K_inv)
+                if row.shape[0] == self.batch_ray:      # fixed-size batches (drop_last): CUDA-graph replay
+                    if getattr(self, "_graphed", None) is None:
+                        self._graphed = GraphedTrainStep(self.model, self.optimizer, self.batch_ray, self.K_inv)
+                    loss, _, _ = self._graphed(row, column, pix_val, poses_bound)
+                    loss = loss.clone()                 # the graph's output buffer is overwritten by the next replay
+                else:
+                    loss, _, _ = train_step(self.model, self.optimizer, row, column, pix_val, poses_bound, self.K_inv)
                 self.scheduler.step()
                 self.losses.append(loss)
                 if ((it + 1) % self.step) == 0:

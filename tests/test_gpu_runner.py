@@ -77,3 +77,44 @@ def test_model_whole_module_pickle():
         a = model(row, col, pb, kinv)[1]
         b = clone(row, col, pb, kinv)[1]
     assert torch.equal(a, b)
+
+
+def test_graphed_train_step_equals_launch_by_launch():
+    """GraphedTrainStep (CUDA-graph replay of forward / loss / backward, Adam outside) against train_step on changing
+    batches.  The learning rate is 0 for the comparison so both paths see the same weights at every step: training itself
+    is chaotic and the loss / split-K weight gradients are summed with fp32 atomics, so trajectories of
+    two runs of EITHER path drift apart; per-step losses and gradients agree to rounding."""
+    from nerf_tiny_b200 import nerf, synth
+    dev = torch.device("cuda:0")
+    rows17 = synth.pose_rows(6, 100, 100, synth.focal_of(100))
+    kinv = synth.k_inv_of(100, 100, synth.focal_of(100))
+    gen = torch.Generator().manual_seed(17)
+    batches = [synth.random_batch(rows17, 256, 100, 100, gen) for _ in range(4)]
+    results = []
+    for graphed in (False, True):
+        nerf.seed_everything(5)
+        model = nerf.NeRFModel(batch_ray=256).to(dev)
+        model.check_range = False
+        model.train()
+        opt = nerf.FusedAdam(model, lr=0.0)
+        step = nerf.GraphedTrainStep(model, opt, 256, kinv) if graphed else None
+        out = []
+        for b in batches:
+            if graphed:
+                loss, _, cf = step(b[0], b[1], b[2], b[3])
+            else:
+                loss, _, cf = nerf.train_step(model, opt, b[0], b[1], b[2], b[3], kinv)
+            out.append((float(loss), cf.clone(), model.network.flat_grads().clone()))
+        model.check_status()
+        results.append(out)
+    for (la, cfa, ga), (lb, cfb, gb) in zip(*results):
+        assert abs(la - lb) <= 1e-5 * abs(la)
+        assert torch.equal(cfa, cfb)                                   # the forward has no atomics: bit-identical
+        assert float((ga - gb).abs().max()) <= 1e-4 * float(ga.abs().max())
+    assert len({round(r[0], 3) for r in results[1]}) == len(batches)   # every replay consumed its own batch
+    # with a real learning rate the optimizer step after the replay moves the weights
+    opt = nerf.FusedAdam(model, lr=1e-3)
+    step = nerf.GraphedTrainStep(model, opt, 256, kinv)
+    before = model.network.flat_params().clone()
+    step(*batches[0][:4])
+    assert not torch.equal(before, model.network.flat_params())
