@@ -124,6 +124,11 @@ int nt_gemm_bf16_debug(nt_ctx* ctx, int mn_major, int m, int n, int k, const voi
  * coarse: delta = (far-near)/Nc for every sample (nerf.py:293).  weights dev [N,Nc], c_out dev [N,3]. */
 int nt_composite_coarse(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, const float* rgb,
                         const float* sigma, float* weights, float* c_out, void* stream);
+/* The two reference methods on their own (NeRFModel.get_density nerf.py:263-272, NeRFModel.color_cum nerf.py:274-281)
+ * for caller-supplied tensors with p samples per ray (multiple of 32, <= 256): delta, sigma, weights dev [N,p];
+ * rgb dev [N,p,3]; c_out dev [N,3].  Inclusive prefix sum accumulated in fp64 and rounded per prefix like the CPU. */
+int nt_get_density(nt_ctx* ctx, int64_t n, int p, const float* delta, const float* sigma, float* weights, void* stream);
+int nt_color_cum(nt_ctx* ctx, int64_t n, int p, const float* weights, const float* rgb, float* c_out, void* stream);
 /* fine: nerf.py:302-321 — concatenate coarse|fine, sort EACH of the 5 channels (t,r,g,b,sigma)
  * independently, delta = diff(t) ++ [last], composite.  perm dev uint8 [N,5,Nc+Nf] or NULL
  * (sorted[i] = in[perm[i]], kept for backward); weights dev [N,Nc+Nf] or NULL. */

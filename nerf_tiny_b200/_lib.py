@@ -46,6 +46,8 @@ SIGNATURES = {
     "nt_mlp_forward_debug": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     "nt_gemm_bf16_debug": (i32, [vp, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp, i32, vp]),
     "nt_composite_coarse": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),
+    "nt_get_density": (i32, [vp, i64, i32, vp, vp, vp, vp]),
+    "nt_color_cum": (i32, [vp, i64, i32, vp, vp, vp, vp]),
     "nt_composite_fine": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp]),
     "nt_composite_coarse_backward": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "nt_composite_fine_backward": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp]),

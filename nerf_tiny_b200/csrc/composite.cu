@@ -91,6 +91,51 @@ __global__ void composite_coarse_kernel(int64_t n, const float* __restrict__ nea
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// piecewise reference methods on caller-supplied tensors: get_density (nerf.py:263-272) and color_cum (nerf.py:274-281),
+// P = 32*EPL samples per ray, one warp per ray, same arithmetic as the fused kernels above
+// ---------------------------------------------------------------------------------------------
+template <int EPL>
+__global__ void get_density_kernel(int64_t n, const float* __restrict__ delta, const float* __restrict__ sigma,
+                                   float* __restrict__ weights) {
+  constexpr int P = EPL * 32;
+  int lane = threadIdx.x & 31;
+  int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ray >= n) return;
+  float a[EPL], w[EPL], te[EPL];
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) a[k] = __fmul_rn(delta[ray * P + lane * EPL + k], sigma[ray * P + lane * EPL + k]);
+  density_weights<EPL>(a, lane, w, te);
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) weights[ray * P + lane * EPL + k] = w[k];
+}
+
+template <int EPL>
+__global__ void color_cum_kernel(int64_t n, const float* __restrict__ weights, const float* __restrict__ rgb,
+                                 float* __restrict__ c_out) {
+  constexpr int P = EPL * 32;
+  int lane = threadIdx.x & 31;
+  int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ray >= n) return;
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) {
+    const int64_t e = ray * P + lane * EPL + k;
+    const float w = weights[e];
+    c0 += w * rgb[e * 3 + 0];
+    c1 += w * rgb[e * 3 + 1];
+    c2 += w * rgb[e * 3 + 2];
+  }
+  c0 = warp_sum(c0);
+  c1 = warp_sum(c1);
+  c2 = warp_sum(c2);
+  if (lane == 0) {
+    c_out[ray * 3 + 0] = c0;
+    c_out[ray * 3 + 1] = c1;
+    c_out[ray * 3 + 2] = c2;
+  }
+}
+
 template <int EPL>
 __global__ void composite_coarse_bwd_kernel(int64_t n, const float* __restrict__ near_, const float* __restrict__ far_,
                                             const float* __restrict__ rgb, const float* __restrict__ sigma,
@@ -343,6 +388,42 @@ extern "C" int nt_composite_coarse(nt_ctx* ctx, int64_t n, const float* near_, c
   if (n <= 0) return NT_OK;
   composite_coarse_kernel<2><<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n, near_, far_, rgb, sigma,
                                                                                        weights, c_out);
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
+
+#define NT_DISPATCH_EPL(P, CALL)                                                     \
+  switch ((P) / 32) {                                                               \
+    case 1: { constexpr int E = 1; CALL; } break;                                   \
+    case 2: { constexpr int E = 2; CALL; } break;                                   \
+    case 3: { constexpr int E = 3; CALL; } break;                                   \
+    case 4: { constexpr int E = 4; CALL; } break;                                   \
+    case 5: { constexpr int E = 5; CALL; } break;                                   \
+    case 6: { constexpr int E = 6; CALL; } break;                                   \
+    case 7: { constexpr int E = 7; CALL; } break;                                   \
+    default: { constexpr int E = 8; CALL; } break;                                  \
+  }
+
+extern "C" int nt_get_density(nt_ctx* ctx, int64_t n, int p, const float* delta, const float* sigma, float* weights,
+                              void* stream) {
+  NT_REQUIRE(ctx, "null ctx");
+  NT_REQUIRE(p > 0 && p <= 256 && p % 32 == 0, "get_density: samples per ray must be a multiple of 32, at most 256");
+  if (n <= 0) return NT_OK;
+  NT_REQUIRE(delta && sigma && weights, "null pointer");
+  const unsigned blocks = (unsigned)((n + 3) / 4);
+  NT_DISPATCH_EPL(p, (get_density_kernel<E><<<blocks, 128, 0, (cudaStream_t)stream>>>(n, delta, sigma, weights)));
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
+
+extern "C" int nt_color_cum(nt_ctx* ctx, int64_t n, int p, const float* weights, const float* rgb, float* c_out,
+                            void* stream) {
+  NT_REQUIRE(ctx, "null ctx");
+  NT_REQUIRE(p > 0 && p <= 256 && p % 32 == 0, "color_cum: samples per ray must be a multiple of 32, at most 256");
+  if (n <= 0) return NT_OK;
+  NT_REQUIRE(weights && rgb && c_out, "null pointer");
+  const unsigned blocks = (unsigned)((n + 3) / 4);
+  NT_DISPATCH_EPL(p, (color_cum_kernel<E><<<blocks, 128, 0, (cudaStream_t)stream>>>(n, weights, rgb, c_out)));
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;
 }

@@ -349,6 +349,26 @@ class NeRFModel(nn.Module):
                                             _ptr(self._packed), _ptr(rgb), _ptr(sigma), _ptr(ws), ws.numel(), 0, _stream()))
         return rgb, sigma
 
+    def get_density(self, delta, sigma):
+        """nerf.py:263-272: w = exp(-cumsum(sigma*delta)) * (1 - exp(-sigma*delta)), [N,P] (P a multiple of 32, <= 256)."""
+        dev = self._ensure_ctx()
+        d, s_ = _dev_f32(delta, dev), _dev_f32(sigma, dev)
+        if s_.dim() == 3:
+            s_ = s_.squeeze(-1).contiguous()
+        n, p = d.shape
+        w = torch.empty(n, p, dtype=torch.float32, device=dev)
+        _lib.check(self._lib.nt_get_density(self._ctx, n, p, _ptr(d), _ptr(s_), _ptr(w), _stream()))
+        return w
+
+    def color_cum(self, density, color):
+        """nerf.py:274-281: C = sum_i w_i * rgb_i, [N,3]."""
+        dev = self._ensure_ctx()
+        w, c = _dev_f32(density, dev), _dev_f32(color, dev)
+        n, p = w.shape
+        out = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        _lib.check(self._lib.nt_color_cum(self._ctx, n, p, _ptr(w), _ptr(c), _ptr(out), _stream()))
+        return out
+
     def resample(self, t_coarse, dense_coarse):
         """nerf.py:225-261 -> t_fine [N,Nf]; raises ResampleRangeError where the reference exits."""
         dev = self._ensure_ctx()

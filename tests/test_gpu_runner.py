@@ -118,3 +118,32 @@ def test_graphed_train_step_equals_launch_by_launch():
     before = model.network.flat_params().clone()
     step(*batches[0][:4])
     assert not torch.equal(before, model.network.flat_params())
+
+
+def test_get_density_and_color_cum_methods():
+    """NeRFModel.get_density / color_cum (nerf.py:263-281) on caller-supplied tensors: against the reference's own
+    coarse-pass outputs (goldens written by the unmodified reference) and against the oracle for 192 merged samples."""
+    import numpy as np
+    from nerf_tiny_b200 import nerf
+    from oracle import nerf_oracle as O
+    dev = torch.device("cuda:0")
+    model = nerf.NeRFModel(batch_ray=8).to(dev)
+    for name in ("lego48_trained", "fern64_trained"):
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+        near, far = torch.from_numpy(g["near"]), torch.from_numpy(g["far"])
+        sigma, color = torch.from_numpy(g["sigma_c"]), torch.from_numpy(g["color_c"])
+        delta = ((far - near) / 64).unsqueeze(1).repeat(1, 64)                   # nerf.py:293
+        w = model.get_density(delta, sigma)
+        assert float((w.cpu() - torch.from_numpy(g["w_c"])).abs().max()) <= 2e-7   # fp64 prefix, 1-ulp expf differences
+        c = model.color_cum(w, color)
+        assert float((c.cpu() - torch.from_numpy(g["c_coarse"])).abs().max()) <= 1e-6
+    gen = torch.Generator().manual_seed(2)
+    delta = torch.rand(37, 192, generator=gen) * 0.05
+    sigma = torch.rand(37, 192, generator=gen) * 30
+    color = torch.rand(37, 192, 3, generator=gen)
+    w = model.get_density(delta, sigma.unsqueeze(-1))                             # sigma [N,P,1] as Network returns it
+    w_ref = O.get_density(delta, sigma)
+    assert float((w.cpu() - w_ref).abs().max()) <= 2e-7
+    assert float((model.color_cum(w, color).cpu() - O.color_cum(w_ref, color)).abs().max()) <= 1e-6
+    with pytest.raises(nerf._lib.NerfTinyError):
+        model.get_density(delta[:, :100], sigma[:, :100])                         # not a multiple of 32
