@@ -83,6 +83,18 @@ int64_t nt_launch_count(const nt_ctx* ctx);
 int nt_raygen(nt_ctx* ctx, int64_t n, const int64_t* row, const int64_t* col, const float* c2w, int c2w_stride,
               const float* kinv, float* rays, float* dir_wrd, float* dir_enc, void* stream);
 
+/* ---- the two sub-modules as the reference exposes them, on caller-supplied tensors ------------
+ * nt_encode: Encoder.forward nerf.py:135-167.  points / dirs dev [total,3] (either may be NULL);
+ *   gamma_point dev [total,3,20], gamma_dir dev [total,3,8] with feature (c, 2l+s) = sin / cos(fl(w_l * x_c)).
+ * nt_network_forward: Network.forward nerf.py:101-124 on those encodings (flattened channel-major to [total,60] and
+ *   [total,24], nerf.py:103-104), fp32 accuracy path.  rgb dev [total,3], sigma dev [total].  Workspace:
+ *   nt_mlp_workspace_bytes(ctx, NT_PREC_FP32, total, 1, 0).  The fused NT_PREC_BF16 path never materialises the
+ *   encodings: use nt_mlp_forward for speed. */
+int nt_encode(nt_ctx* ctx, int64_t total, const float* points, const float* dirs, float* gamma_point, float* gamma_dir,
+              void* stream);
+int nt_network_forward(nt_ctx* ctx, int64_t total, const float* enc_point, const float* enc_dir, const float* params,
+                       float* rgb, float* sigma, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- coarse samples: nerf.py:288  np.linspace(near, far, Nc) in fp32 -------------------
  * any_step_zero: -1 = decide on this launch's rays (numpy's batch-global branch), 0/1 = forced
  * (multi-GPU shards pass the globally reduced flag).  t_coarse dev [N,Nc]. */

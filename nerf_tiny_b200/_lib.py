@@ -37,6 +37,8 @@ SIGNATURES = {
     "nt_launch_count": (i64, [vp]),
     "nt_set_option": (i32, [vp, i32, i32]),
     "nt_raygen": (i32, [vp, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
+    "nt_encode": (i32, [vp, i64, vp, vp, vp, vp, vp]),
+    "nt_network_forward": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, sz, vp]),
     "nt_sample_coarse": (i32, [vp, i64, vp, vp, i32, vp, vp]),
     "nt_mlp_workspace_bytes": (sz, [vp, i32, i64, i32, i32]),
     "nt_packed_weight_bytes": (sz, [vp, i32]),

@@ -282,6 +282,16 @@ static int nt_launch_axpy(nt_ctx* ctx, int64_t n, const float* x, float* y, cuda
   return NT_OK;
 }
 
+// Network.forward (nerf.py:101-124) as the reference exposes it: caller-supplied encodings, fp32 accuracy path.
+// The workspace is that of nt_mlp_workspace_bytes(ctx, NT_PREC_FP32, total, 1, 0).
+extern "C" int nt_network_forward(nt_ctx* ctx, int64_t total, const float* enc_point, const float* enc_dir,
+                                  const float* params, float* rgb, float* sigma, void* ws, size_t ws_bytes, void* stream) {
+  NT_REQUIRE(ctx, "null ctx");
+  if (total <= 0) return NT_OK;
+  NT_REQUIRE(enc_point && enc_dir && params && rgb && sigma && ws, "null pointer");
+  return nt_network_f32_forward(ctx, total, enc_point, enc_dir, params, rgb, sigma, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 // diagnostic: NT_PREC_BF16 forward that also dumps one MMA layer's post-activation fp32 output (dbg dev [N*P,256];
 // layer 0..7 = trunk, 8 = point_info, 9 = dir_info) — used by the layer-by-layer parity test
 extern "C" int nt_mlp_forward_debug(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays,

@@ -111,6 +111,8 @@ int nt_launch_colsum(nt_ctx* ctx, const float* G, int64_t rows, int cols, int ld
 
 // mlp_f32.cu
 size_t nt_mlp_f32_workspace_bytes(int64_t n, int p, int train);
+int nt_network_f32_forward(nt_ctx* ctx, int64_t S, const float* enc_point, const float* enc_dir, const float* params,
+                           float* rgb, float* sigma, void* ws, size_t ws_bytes, cudaStream_t st);
 int nt_mlp_f32_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                        const float* params, float* rgb, float* sigma, void* ws, size_t ws_bytes, int train,
                        cudaStream_t st);

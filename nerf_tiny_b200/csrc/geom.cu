@@ -127,6 +127,25 @@ __global__ void encode_points_kernel(int64_t total, int p, const float* __restri
   }
 }
 
+// Encoder.forward (nerf.py:135-167) on caller-supplied coordinates: x [S,3] -> out [S,3,2L], feature (c, 2l+s) =
+// sin / cos of fl(w_l * x_c); thread = (sample, channel)
+template <int L>
+__global__ void encode_generic_kernel(int64_t total, const float* __restrict__ x, const uint32_t* __restrict__ freq_unused,
+                                      float* __restrict__ out) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total * 3) return;
+  const float v = x[gid];
+  float* o = out + gid * (2 * L);
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const float w = __uint_as_float(L == 10 ? c_freq_point[l] : c_freq_dir[l]);
+    float sn, cs;
+    sincosf(__fmul_rn(w, v), &sn, &cs);
+    o[2 * l] = sn;
+    o[2 * l + 1] = cs;
+  }
+}
+
 __global__ void expand_dir_enc_kernel(int64_t total, int p, const float* __restrict__ dir_enc, float* __restrict__ out,
                                       int ld) {
   int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -227,6 +246,25 @@ int nt_launch_encode_points(nt_ctx* ctx, int64_t n, int p, const float* t, const
   if (total <= 0) return NT_OK;
   encode_points_kernel<<<(unsigned)((total * 3 + 255) / 256), 256, 0, st>>>(total, p, t, rays, enc, ld_enc);
   NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
+
+extern "C" int nt_encode(nt_ctx* ctx, int64_t total, const float* points, const float* dirs, float* gamma_point,
+                         float* gamma_dir, void* stream) {
+  NT_REQUIRE(ctx, "null ctx");
+  if (total <= 0) return NT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((total * 3 + 255) / 256);
+  if (points) {
+    NT_REQUIRE(gamma_point, "null output pointer");
+    encode_generic_kernel<10><<<blocks, 256, 0, st>>>(total, points, nullptr, gamma_point);
+    NT_LAUNCH_CHECK(ctx);
+  }
+  if (dirs) {
+    NT_REQUIRE(gamma_dir, "null output pointer");
+    encode_generic_kernel<4><<<blocks, 256, 0, st>>>(total, dirs, nullptr, gamma_dir);
+    NT_LAUNCH_CHECK(ctx);
+  }
   return NT_OK;
 }
 

@@ -89,12 +89,20 @@ static const GemmSeg kNoSeg = {nullptr, 0, nullptr, 0, 0};
     if (rc__ != NT_OK) return rc__; \
   } while (0)
 
+static int forward_from_enc(nt_ctx* ctx, int S, const float* P, float* rgb, float* sigma, F32Ws& w, bool train,
+                            cudaStream_t st);
+
 static int forward_chunk(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                          const float* P, float* rgb, float* sigma, F32Ws& w, bool train, cudaStream_t st) {
-  const LayerTable L = nt_layers();
-  const int S = (int)(n * p);
   NT_TRY(nt_launch_encode_points(ctx, n, p, t, rays, w.enc, 60, st));
   NT_TRY(nt_launch_expand_dir_enc(ctx, n, p, dir_enc, w.denc, 24, st));
+  return forward_from_enc(ctx, (int)(n * p), P, rgb, sigma, w, train, st);
+}
+
+// Network.forward (nerf.py:101-124) on the dense feature matrices w.enc [S,60] / w.denc [S,24]
+static int forward_from_enc(nt_ctx* ctx, int S, const float* P, float* rgb, float* sigma, F32Ws& w, bool train,
+                            cudaStream_t st) {
+  const LayerTable L = nt_layers();
   // L0 (nerf.py:85, :111)
   NT_TRY(nt_launch_gemm(ctx, S, 256, seg_of(w.enc, 60, P + L.w[L_P0], 60, 60), kNoSeg, false, false, w.h[0], 256,
                         epi_of(P + L.b[L_P0], ACT_RELU), 1, st));
@@ -151,6 +159,24 @@ int nt_mlp_f32_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const floa
     F32Ws w = carve_f32(ws, nr * p, false);
     NT_TRY(forward_chunk(ctx, nr, p, t + r0 * p, rays + r0 * 16, dir_enc + r0 * 24, params, rgb + r0 * p * 3,
                          sigma + r0 * p, w, false, st));
+  }
+  return NT_OK;
+}
+
+// Network.forward on caller-supplied encodings (the reference's stand-alone module call): fp32, render-only, chunked
+int nt_network_f32_forward(nt_ctx* ctx, int64_t S, const float* enc_point, const float* enc_dir, const float* params,
+                           float* rgb, float* sigma, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int64_t chunk = F32_RENDER_CHUNK_SAMPLES;
+  if (ws_bytes < carve_f32(nullptr, S < chunk ? S : chunk, false).bytes) {
+    nt_set_error("network forward workspace too small");
+    return NT_ERR_WORKSPACE;
+  }
+  for (int64_t s0 = 0; s0 < S; s0 += chunk) {
+    const int64_t ns = S - s0 < chunk ? S - s0 : chunk;
+    F32Ws w = carve_f32(ws, ns, false);
+    w.enc = const_cast<float*>(enc_point) + s0 * 60;   // read-only in the forward
+    w.denc = const_cast<float*>(enc_dir) + s0 * 24;
+    NT_TRY(forward_from_enc(ctx, (int)ns, params, rgb + s0 * 3, sigma + s0, w, false, st));
   }
   return NT_OK;
 }

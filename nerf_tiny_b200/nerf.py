@@ -62,6 +62,22 @@ def _dev_f32(t, dev):
     return t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
 
 
+_MODULE_CTX = {}
+
+
+def _module_ctx(dev):
+    """A library context for stand-alone sub-module calls (Encoder / Network used outside a NeRFModel)."""
+    if dev.type != "cuda":
+        raise _lib.NerfTinyError("this module lives on %s: move it to a CUDA device (no CPU path exists)" % dev)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _MODULE_CTX:
+        lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(lib.nt_create(C.byref(h), idx, 64, 128))
+        _MODULE_CTX[idx] = (lib, h)
+    return _MODULE_CTX[idx]
+
+
 class Activation(nn.Module):
     """nerf.py:69-74 (sigma = |x|).  Fused into the MLP kernels; kept for state_dict/module-tree parity."""
 
@@ -152,8 +168,21 @@ class Network(nn.Module):
         return self._flat_grad
 
     def forward(self, num_points, point, dir):
-        raise _lib.NerfTinyError(
-            "Network.forward on pre-computed encodings is not part of the fused path; use NeRFModel.net_out")
+        """nerf.py:101-124 on materialised encodings point [N,P,3,20], dir [N,P,3,8] -> (color [N,P,3], sigma [N,P,1]).
+        fp32 accuracy path (nt_network_forward), no autograd: training goes through NeRFModel.forward, whose fused kernels
+        never write the encodings to memory."""
+        flat = self.flat_params()
+        lib, h = _module_ctx(flat.device)
+        n, p = point.shape[0], point.shape[1]
+        enc_p = _dev_f32(point, flat.device).reshape(n * p, 60)      # flatten(start_dim=2): channel-major (nerf.py:103)
+        enc_d = _dev_f32(dir, flat.device).reshape(n * p, 24)
+        color = torch.empty(n, p, 3, dtype=torch.float32, device=flat.device)
+        sigma = torch.empty(n, p, 1, dtype=torch.float32, device=flat.device)
+        need = max(256, lib.nt_mlp_workspace_bytes(h, _lib.PREC_FP32, n * p, 1, 0))
+        ws = torch.empty(need, dtype=torch.uint8, device=flat.device)
+        _lib.check(lib.nt_network_forward(h, n * p, _ptr(enc_p), _ptr(enc_d), _ptr(flat.detach()), _ptr(color), _ptr(sigma),
+                                          _ptr(ws), ws.numel(), _stream()))
+        return color, sigma
 
 
 class Encoder(nn.Module):
@@ -167,7 +196,18 @@ class Encoder(nn.Module):
         self.L_point, self.L_dir, self.batch_size = L_point, L_dir, batch_size
 
     def forward(self, num_points, point, dir):
-        raise _lib.NerfTinyError("Encoder.forward is fused into the CUDA MLP kernels; use NeRFModel.net_out")
+        """nerf.py:135-167: point, dir [N,P,3] -> (gamma_point [N,P,3,20], gamma_dir [N,P,3,8]) on the CUDA device.  Like the
+        reference, 14 numbers are drawn from the global CPU generator and thrown away (nerf.py:141) so that code sharing
+        that generator sees the same stream.  The fused render path does not call this (it never materialises them)."""
+        torch.rand(1, 1, self.L_point + self.L_dir, 1, 1)
+        dev = device if (device is not None and device.type == "cuda") else torch.device("cuda", torch.cuda.current_device())
+        lib, h = _module_ctx(dev)
+        n, p = point.shape[0], point.shape[1]
+        pt, dr = _dev_f32(point, dev), _dev_f32(dir, dev)
+        g_p = torch.empty(n, p, 3, 2 * self.L_point, dtype=torch.float32, device=dev)
+        g_d = torch.empty(n, p, 3, 2 * self.L_dir, dtype=torch.float32, device=dev)
+        _lib.check(lib.nt_encode(h, n * p, _ptr(pt), _ptr(dr), _ptr(g_p), _ptr(g_d), _stream()))
+        return g_p, g_d
 
 
 class _RenderFn(torch.autograd.Function):

@@ -147,3 +147,34 @@ def test_get_density_and_color_cum_methods():
     assert float((model.color_cum(w, color).cpu() - O.color_cum(w_ref, color)).abs().max()) <= 1e-6
     with pytest.raises(nerf._lib.NerfTinyError):
         model.get_density(delta[:, :100], sigma[:, :100])                         # not a multiple of 32
+
+
+def test_encoder_and_network_standalone_modules():
+    """Encoder.forward / Network.forward called the way the reference exposes them (nerf.py:101-167), against the outputs
+    the unmodified reference wrote for the same inputs and weights (tests/golden/encoder_network.npz)."""
+    import numpy as np
+    from nerf_tiny_b200 import nerf
+    from oracle import nerf_oracle as O
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "encoder_network.npz"))
+    pts, dirs = torch.from_numpy(g["pts"]), torch.from_numpy(g["dirs"])
+    model = nerf.NeRFModel(batch_ray=pts.shape[0])
+    model.load_state_dict(O.trained_like(O.init_state_dict(624)))
+    model = model.to(dev)
+    nerf.device = dev
+    state = torch.get_rng_state()
+    gp, gd = model.encoder(pts.shape[1], pts, dirs)
+    after = torch.get_rng_state()
+    torch.set_rng_state(state)
+    torch.rand(1, 1, 14, 1, 1)
+    assert torch.equal(after, torch.get_rng_state())                    # same 14 draws as nerf.py:141
+    assert gp.shape == (4, 16, 3, 20) and gd.shape == (4, 16, 3, 8)
+    # CUDA sincosf vs ATen's CPU sin / cos: arguments reach |w x| ~ 2e4, both are correctly reduced, results differ by ulps
+    assert float((gp.flatten(start_dim=2).cpu() - torch.from_numpy(g["point_enc"])).abs().max()) <= 5e-7
+    assert float((gd.flatten(start_dim=2).cpu() - torch.from_numpy(g["dir_enc"])).abs().max()) <= 5e-7
+    ref_gp = torch.from_numpy(g["point_enc"]).reshape(4, 16, 3, 20)
+    ref_gd = torch.from_numpy(g["dir_enc"]).reshape(4, 16, 3, 8)
+    color, sigma = model.network(pts.shape[1], ref_gp, ref_gd)
+    assert color.shape == (4, 16, 3) and sigma.shape == (4, 16, 1)
+    assert float((color.cpu() - torch.from_numpy(g["color"])).abs().max()) <= 5e-6
+    assert float((sigma.cpu() - torch.from_numpy(g["sigma"])).abs().max()) <= 5e-6 * max(1.0, float(np.abs(g["sigma"]).max()))
