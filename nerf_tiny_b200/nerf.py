@@ -622,6 +622,8 @@ class GraphedTrainStep:
 # resident in HBM) when an image folder is given, or from any iterable of loader-shaped tuples.
 # ----------------------------------------------------------------------------------------------------
 class NeRFRunner():
+    DISPLAY_RAYS = 1 << 16      # rays per render launch of display()
+
     def __init__(self, gpu=0, img_dir=None, results_path="./results/", ckpt_path="./checkpoint/", low_res=1,
                  total_iter=100000, batch_ray=400, learning=1e-3, lr_gamma=0.1, lr_milestone=[10, 200], n_coarse=64,
                  n_fine=128, data_type="llff", step=100, decay_end=200000, sched="EXP", continue_=False,
@@ -665,7 +667,10 @@ class NeRFRunner():
                 self.val_dataset = loader.NeRFDataset(root_dir=img_dir, low_res=low_res, type=data_type, mode="val")
                 self.disp_dataset = loader.NeRFDataset(root_dir=img_dir, low_res=low_res, type=data_type, mode="test")
                 self.val_dataloader = loader.GpuRayBatches.from_dataset(self.val_dataset, batch_ray, shuffle=True, device=device)
-                disp_batches = loader.GpuRayBatches.from_dataset(self.disp_dataset, batch_ray, shuffle=False, device=device)
+                # display: every pixel in flat order, tiled into launches large enough to fill the GPU (the reference's
+                # batch_ray-sized, drop_last display loader leaves the tail of the last view white, nerf.py:442)
+                disp_batches = loader.GpuRayBatches.from_dataset(self.disp_dataset, max(batch_ray, self.DISPLAY_RAYS),
+                                                                 shuffle=False, drop_last=False, device=device)
                 num_pic = self.disp_dataset.pic_num
             except (FileNotFoundError, OSError):
                 self.val_dataloader, disp_batches = train_batches, None
@@ -695,6 +700,23 @@ class NeRFRunner():
         torch.save({"model": sd, "optimizer": self.optimizer.state_dict(), "iter": it}, path)
         return path
 
+    def _flush_losses(self, it):
+        """The reference logs a TensorBoard scalar per step (a host sync each, nerf.py:478); here the per-step losses stay
+        on the device and are appended to <results_path><start_time>_loss.csv once every `step` iterations (and to
+        nerf.writer, if the caller installed a SummaryWriter-like object there)."""
+        if not self.losses:
+            return
+        vals = torch.cat([l.reshape(1) for l in self.losses]).cpu().tolist()
+        first = it - len(vals) + 1
+        os.makedirs(os.path.dirname(self.results_path) or ".", exist_ok=True)
+        with open(self.results_path + self.start_time + "_loss.csv", "a") as f:
+            for k, v in enumerate(vals):
+                f.write("%d,%.6f\n" % (first + k, v))
+                if writer is not None:
+                    writer.add_scalar("Loss/train", v, first + k)
+        self.last_loss = vals[-1]
+        self.losses = []
+
     def trainer(self, mode):
         """nerf.py:445-499 loop body (forward, ray_loss, backward, Adam, scheduler) over the batch source; the loss is
         kept on the device (no per-step host sync), a checkpoint is written every `step` iterations."""
@@ -714,6 +736,7 @@ class NeRFRunner():
                 self.losses.append(loss)
                 if ((it + 1) % self.step) == 0:
                     print("\n[ITER]", it, " [LOSS] %.4f" % float(loss))
+                    self._flush_losses(it)
                     self.save_checkpoint(it)
                 it += 1
                 n_seen += 1
@@ -722,11 +745,13 @@ class NeRFRunner():
             if mode == "val" or n_seen == 0:
                 break
         self.last_iter = it - 1
+        self._flush_losses(self.last_iter)
         self.model.check_status()
 
     def display(self, save=False):
         """nerf.py:503-530: no-grad render of every test batch, scattered into (num_pic, H, W, 3); with save=True the
-        frames are written as <results_path><start_time>/<i>.jpg (uint8 conversion on the GPU)."""
+        frames are written as <results_path><start_time>/<i>.jpg plus an animated video.gif (the reference writes video.mp4
+        through imageio, nerf.py:528; PIL is what this image has), uint8 conversion on the GPU."""
         result = torch.full((self.num_pic, self.height, self.width, 3), 1.0, device=device)
         with torch.no_grad():
             self.model.eval()
@@ -738,6 +763,9 @@ class NeRFRunner():
             out_dir = self.results_path + self.start_time + "/"
             os.makedirs(out_dir, exist_ok=True)
             frames = (result.clamp(0, 1) * 255.0).to(torch.uint8).cpu().numpy()
-            for i in range(self.num_pic):
-                Image.fromarray(frames[i]).save(out_dir + str(i) + ".jpg")
+            images = [Image.fromarray(frames[i]) for i in range(self.num_pic)]
+            for i, im in enumerate(images):
+                im.save(out_dir + str(i) + ".jpg")
+            if len(images) > 1:
+                images[0].save(out_dir + "video.gif", save_all=True, append_images=images[1:], duration=33, loop=0)
         return result

@@ -39,7 +39,8 @@ def test_runner_train_checkpoint_resume_display(tmp_path):
     r1 = nerf.NeRFRunner(total_iter=8, continue_=False, **kw)
     assert r1.height == 16 and r1.num_pic == 2 and len(r1.train_dataloader) == 8
     r1.trainer("train")
-    assert len(r1.losses) == 8 and all(np.isfinite(float(l)) for l in r1.losses)
+    rows = [l.split(",") for l in open(glob.glob(res + "*_loss.csv")[0]).read().split()]
+    assert [int(r[0]) for r in rows] == list(range(8)) and all(np.isfinite(float(r[1])) for r in rows)
     files = sorted(glob.glob(ck + "*.pkl"))
     assert [int(f.split("_")[-1][:-4]) for f in files] == [3, 7]
     w_end = r1.model.network.flat_params().clone()
@@ -51,12 +52,14 @@ def test_runner_train_checkpoint_resume_display(tmp_path):
     assert torch.equal(r2.optimizer.m.to(w_end.device), m_end)
     assert abs(r2.optimizer.param_groups[0]["lr"] - 1e-3 * 0.1 ** (8 / 1000)) < 1e-12
     r2.trainer("train")
-    assert len(r2.losses) == 2 and r2.last_iter == 9
+    assert r2.last_iter == 9 and np.isfinite(r2.last_loss)
+    assert len(open(glob.glob(res + r2.start_time + "_loss.csv")[0]).read().split()) in (2, 10)   # same second -> same file
     assert not torch.equal(r2.model.network.flat_params(), w_end)
 
     img = r2.display(save=True)
     assert img.shape == (2, 16, 16, 3) and bool(torch.isfinite(img).all())
-    assert len(glob.glob(res + "*/*.jpg")) == 2
+    assert len(glob.glob(res + "*/*.jpg")) == 2 and len(glob.glob(res + "*/video.gif")) == 1
+    assert float((img - 1.0).abs().max()) > 0 and bool((img != 1.0).reshape(2, -1).any(dim=1).all())   # every view rendered
 
 
 def test_model_whole_module_pickle():
