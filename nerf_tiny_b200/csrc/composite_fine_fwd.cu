@@ -29,38 +29,65 @@ __device__ __forceinline__ float tmax(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ float shfl_x(float v, int m) { return __shfl_xor_sync(FULL, v, m); }
 __device__ __forceinline__ unsigned long long shfl_x(unsigned long long v, int m) { return __shfl_xor_sync(FULL, v, m); }
 
-// ascending bitonic sort of 256 elements, element e = lane*8 + r
+// ascending bitonic sort of 256 elements, element e = lane*8 + r, in the direction-free formulation: the first round of
+// merge stage k pairs e with its mirror e ^ (k-1) inside the k-block (two ascending halves -> bitonic split), the
+// remaining rounds pair e with e ^ j; every compare-exchange is ascending (the lower index keeps the minimum).  Pairs
+// inside a lane are compile-time (two FMNMX, no select); pairs across lanes cost one shuffle and one min-or-max chosen
+// by a lane predicate.
 template <typename T>
-__device__ __noinline__ void warp_sort_256(T (&v)[8], int lane) {
+__device__ __forceinline__ void warp_sort_256(T (&v)[8], int lane) {
 #pragma unroll
   for (int k = 2; k <= 256; k <<= 1) {
+    // ---- mirror round: partner e ^ (k-1)
+    if (k <= 8) {
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int r = 0; r < 8; ++r) {
+        const int q = r ^ (k - 1);
+        if (r < q) {
+          const T a = v[r], b = v[q];
+          v[r] = tmin(a, b);
+          v[q] = tmax(a, b);
+        }
+      }
+    } else {
+      const int m = (k >> 3) - 1;                       // partner lane = lane ^ m, partner register = 7 - r
+      const bool lower = (lane & (k >> 4)) == 0;
+      T o[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) o[r] = shfl_x(v[7 - r], m);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = lower ? tmin(v[r], o[r]) : tmax(v[r], o[r]);
+    }
+    // ---- half-cleaner rounds: partner e ^ j, j = k/4 .. 1
+#pragma unroll
+    for (int j = k >> 2; j > 0; j >>= 1) {
       if (j >= 8) {
         const int m = j >> 3;
         const bool lower = (lane & m) == 0;
-        const bool up = ((lane << 3) & k) == 0;
-        const bool keep_min = lower == up;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const T o = shfl_x(v[r], m);
-          v[r] = keep_min ? tmin(v[r], o) : tmax(v[r], o);
+          v[r] = lower ? tmin(v[r], o) : tmax(v[r], o);
         }
       } else {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           if ((r & j) == 0) {
-            const bool up = k >= 8 ? (((lane << 3) & k) == 0) : ((r & k) == 0);
             const T a = v[r], b = v[r | j];
-            const T lo = tmin(a, b), hi = tmax(a, b);
-            v[r] = up ? lo : hi;
-            v[r | j] = up ? hi : lo;
+            v[r] = tmin(a, b);
+            v[r | j] = tmax(a, b);
           }
         }
       }
     }
   }
 }
+
+// The float instantiation is inlined five times (keys stay in registers: as an out-of-line call the array lived in local
+// memory and the kernel was bound by the LSU pipe - 445 local stores per ray next to its 600 shuffles; inlining took the
+// 160000-ray render launch from 1.17 to ~0.6 ms).  The 64-bit (key, index) instantiation of the training path is
+// register-hungry (95 registers inlined) and is faster out of line.
+__device__ __noinline__ void warp_sort_256_call(unsigned long long (&v)[8], int lane) { warp_sort_256<unsigned long long>(v, lane); }
 
 __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
 #pragma unroll
@@ -133,7 +160,7 @@ __global__ void __launch_bounds__(128) composite_fine_fwd_kernel(int64_t n, cons
       unsigned long long kv[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) kv[r] = ((unsigned long long)f2ord(ch[c][r]) << 32) | (unsigned)(lane * 8 + r);
-      warp_sort_256<unsigned long long>(kv, lane);
+      warp_sort_256_call(kv, lane);
       uint32_t lo = 0, hi = 0;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
