@@ -178,48 +178,6 @@ __global__ void __launch_bounds__(128) heads_backward_kernel(int64_t S, const fl
   atomicAdd(db_dir + col, (part[0][col] + part[1][col]) + (part[2][col] + part[3][col]));
 }
 
-// column sums of a bf16 matrix [rows][ld] accumulated (fp32 atomics) into out[cols]; cols even.
-// One thread per column PAIR (bf16x2 loads: a warp reads 128 contiguous bytes per row), 4 rows in flight per thread.
-__global__ void __launch_bounds__(128) colsum_bf16_kernel(const bf16* __restrict__ G, int64_t rows, int cols, int ld,
-                                                           float* __restrict__ out, int rows_per_block) {
-  const int cp = threadIdx.x;
-  if (2 * cp >= cols) return;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  int64_t r1 = r0 + rows_per_block;
-  if (r1 > rows) r1 = rows;
-  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;
-  const uint32_t* base = reinterpret_cast<const uint32_t*>(G) + cp;
-  const int64_t ldw = ld / 2;
-  int64_t r = r0;
-  for (; r + 3 < r1; r += 4) {
-    const uint32_t w0 = __ldg(base + r * ldw), w1 = __ldg(base + (r + 1) * ldw), w2 = __ldg(base + (r + 2) * ldw),
-                   w3 = __ldg(base + (r + 3) * ldw);
-    a0 += __uint_as_float(w0 << 16);
-    a1 += __uint_as_float(w0 & 0xffff0000u);
-    b0 += __uint_as_float(w1 << 16);
-    b1 += __uint_as_float(w1 & 0xffff0000u);
-    c0 += __uint_as_float(w2 << 16);
-    c1 += __uint_as_float(w2 & 0xffff0000u);
-    d0 += __uint_as_float(w3 << 16);
-    d1 += __uint_as_float(w3 & 0xffff0000u);
-  }
-  for (; r < r1; ++r) {
-    const uint32_t w0 = __ldg(base + r * ldw);
-    a0 += __uint_as_float(w0 << 16);
-    a1 += __uint_as_float(w0 & 0xffff0000u);
-  }
-  atomicAdd(out + 2 * cp, (a0 + b0) + (c0 + d0));
-  if (2 * cp + 1 < cols) atomicAdd(out + 2 * cp + 1, (a1 + b1) + (c1 + d1));
-}
-
-int colsum_bf16(nt_ctx* ctx, const bf16* G, int64_t rows, int cols, int ld, float* out, cudaStream_t st) {
-  const int rpb = 128;
-  const unsigned blocks = (unsigned)((rows + rpb - 1) / rpb);
-  colsum_bf16_kernel<<<blocks, 128, 0, st>>>(G, rows, cols, ld, out, rpb);
-  NT_LAUNCH_CHECK(ctx);
-  return NT_OK;
-}
-
 GemmTcEpi epi0() {
   GemmTcEpi e;
   memset(&e, 0, sizeof(e));
