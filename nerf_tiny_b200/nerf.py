@@ -725,7 +725,7 @@ class NeRFRunner():
         while it < self.total_iter:
             n_seen = 0
             for (row, column, pix_val, poses_bound, pic) in dataloader:
-                if row.shape[0] == self.batch_ray:      # fixed-size batches (drop_last): CUDA-graph replay
+                if row.shape[0] == self.batch_ray and self.model.precision == "bf16":   # fixed-size batches: graph replay
                     if getattr(self, "_graphed", None) is None:
                         self._graphed = GraphedTrainStep(self.model, self.optimizer, self.batch_ray, self.K_inv)
                     loss, _, _ = self._graphed(row, column, pix_val, poses_bound)
