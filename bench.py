@@ -231,9 +231,10 @@ def run_b200(args):
     d2h = out_host.numel() * 4
 
     # ---- dominant kernel alone: fused encode+MLP (fine pass, 128 samples/ray), CUDA events on its stream --
-    roof = None
+    roof, roof_hbm = None, None
     if rank == 0:
         roof = mlp_roofline(model, dev, d_row, d_col, d_pb, d_kinv, flat, flush)
+        roof_hbm = hbm_rooflines(model, dev, flush, N_RAYS)
 
     # ---- training step (extra): reference loop body nerf.py:464-475 through train_step ------------------
     train = None
@@ -266,7 +267,7 @@ def run_b200(args):
             "mlp_tc_frac_of_peak": value / world * FLOP_PER_RAY_RENDER / (pk["tf"] * 1e12),
             "e2e": {"value": world * N_RAYS / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "train": train, "clocks": clocks,
+            "gpu_launches": launches, "roofline": roof, "roofline_hbm_kernels": roof_hbm, "cpu_baseline": cpu, "train": train, "clocks": clocks,
             "peaks": pk,
         }
         print(json.dumps(out))
@@ -319,6 +320,51 @@ def mlp_roofline(model, dev, d_row, d_col, d_pb, d_kinv, flat, flush, iters=5):
             # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture summarised in
             # profiles/r1j_mlp_tc7_summary.txt (110.8 MB + 277.2 MB); algorithmic bytes = 4 B t + 16 B rgb/sigma per sample
             "traffic": 388.0e6 if prec == 2 else None, "traffic_unit": "B per launch (ncu, profiles/r1j_mlp_tc7_summary.txt)"}
+
+
+def hbm_rooflines(model, dev, flush, n, iters=5):
+    """The per-ray HBM-bound kernels of the render step alone (CUDA events on their stream, L2 flushed before each): achieved
+    GB/s = SURVEY.md §8(d)'s algorithmic bytes per ray x rays / launch time, against the measured HBM peak."""
+    from nerf_tiny_b200 import _lib
+    import ctypes as C
+    L, h = model._lib, model._ctx
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device=dev).manual_seed(7)
+    near, far = torch.full((n,), 2.0, device=dev), torch.full((n,), 6.0, device=dev)
+    t_c = torch.empty(n, 64, device=dev)
+    _lib.check(L.nt_sample_coarse(h, n, p(near), p(far), -1, p(t_c), st))
+    rgb_c, sig_c = torch.rand(n, 64, 3, device=dev, generator=g), torch.rand(n, 64, device=dev, generator=g) * 3
+    rgb_f, sig_f = torch.rand(n, 128, 3, device=dev, generator=g), torch.rand(n, 128, device=dev, generator=g) * 3
+    w_c, c_c, c_f = torch.empty(n, 64, device=dev), torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
+    t_f = torch.empty(n, 128, device=dev)
+    calls = [
+        ("composite_coarse_kernel (get_density + color_cum, 64 samples)", 1300,
+         lambda: L.nt_composite_coarse(h, n, p(near), p(far), p(rgb_c), p(sig_c), p(w_c), p(c_c), st)),
+        ("sample_pdf_kernel (cdf, searchsorted, interpolation)", 776,
+         lambda: L.nt_sample_pdf(h, n, p(t_c), p(w_c), None, p(t_f), None, st)),
+        ("composite_fine_fwd_kernel (merge, 5 channel sorts, compositing, 192 samples)", 3852,
+         lambda: L.nt_composite_fine(h, n, p(t_c), p(rgb_c), p(sig_c), p(t_f), p(rgb_f), p(sig_f), 1e-4, p(c_f), None, None, st)),
+    ]
+    pk = peaks()
+    out = []
+    for name, bytes_per_ray, fn in calls:
+        for _ in range(2):
+            _lib.check(fn())
+        ms = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(fn())
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        dur = float(np.mean(ms)) * 1e-3
+        ach = n * bytes_per_ray / dur / 1e9
+        out.append({"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                    "launch_us": dur * 1e6, "algorithmic_bytes_per_ray": bytes_per_ray})
+    return out
 
 
 def bench_train(model, dev, rows17, world, rank, barrier, args):
