@@ -37,6 +37,8 @@ FLOP_PER_RAY_RENDER = FLOP_PER_SAMPLE * SAMPLES_PER_RAY          # 227.131 MFLOP
 FLOP_PER_RAY_TRAIN = 676.282e6
 WORKLOAD = "lego.ini coarse64+fine128 render of a 400x400 synthetic Blender-shape view (160000 rays)"
 TRAIN_BATCH = 1024
+# arithmetic type of the MLP contraction per --precision (accumulation is fp32 everywhere)
+DTYPE = {"fp16": "fp16", "bf16": "bf16", "tc32": "fp16x3 (split fp16, fp32-tolerance mode)", "fp32": "f32"}
 
 
 def peaks():
@@ -258,7 +260,7 @@ def run_b200(args):
         out = {
             "metric": "rays/sec (render, coarse64+fine128)", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.precision],
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": N_RAYS, "samples_per_ray": "64+128",
                        "weights": "random init (nn.Linear default), 593924 params", "precision": args.precision,
@@ -292,10 +294,10 @@ def mlp_roofline(model, dev, d_row, d_col, d_pb, d_kinv, flat, flush, iters=5):
     prec = model._prec
     need = max(256, L.nt_mlp_workspace_bytes(h, prec, n, 128, 0))
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
-    model._pack(flat)
+    packed = model._pack(flat, prec)
 
     def go():
-        _lib.check(L.nt_mlp_forward(h, prec, n, 128, p(t), p(rays), p(denc), p(flat), p(model._packed), p(rgb), p(sig),
+        _lib.check(L.nt_mlp_forward(h, prec, n, 128, p(t), p(rays), p(denc), p(flat), p(packed) if packed is not None else None, p(rgb), p(sig),
                                     p(ws), ws.numel(), 0, st))
     for _ in range(3):
         go()
@@ -313,13 +315,13 @@ def mlp_roofline(model, dev, d_row, d_col, d_pb, d_kinv, flat, flush, iters=5):
     flops = FLOP_PER_SAMPLE * n * 128
     pk = peaks()
     ach = flops / dur / 1e12
-    return {"kernel": "mlp_tc7_kernel (fused encode + 8x256 MLP, cta_group::2 schedule, fine pass 128 samples/ray)" if prec == 2 else
-            "gemm_f32_kernel chain (fp32 accuracy path)", "bound": "tensor", "achieved": ach, "peak": pk["tf"],
+    return {"kernel": "mlp_tc7_kernel (fused encode + 8x256 MLP, cta_group::2 schedule, fine pass 128 samples/ray)" if prec in (2, 3) else
+            ("mlp_tc32_kernel (3-pass split-fp16)" if prec == 1 else "gemm_f32_kernel chain (fp32 accuracy path)"), "bound": "tensor", "achieved": ach, "peak": pk["tf"],
             "unit": "TFLOP/s", "frac": ach / pk["tf"], "frac_of_sustained": ach / pk["tf_sustained"] if pk["tf_sustained"] else None,
             "peak_source": pk["src"] + " bf16 burst", "launch_ms": dur * 1e3, "algorithmic_flop_per_launch": flops,
             # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture summarised in
             # profiles/r1j_mlp_tc7_summary.txt (110.8 MB + 277.2 MB); algorithmic bytes = 4 B t + 16 B rgb/sigma per sample
-            "traffic": 388.0e6 if prec == 2 else None, "traffic_unit": "B per launch (ncu, profiles/r1j_mlp_tc7_summary.txt)"}
+            "traffic": 388.0e6 if prec in (2, 3) else None, "traffic_unit": "B per launch (ncu, profiles/r1j_mlp_tc7_summary.txt)"}
 
 
 def hbm_rooflines(model, dev, flush, n, iters=5):
@@ -412,7 +414,7 @@ def bench_train(model, dev, rows17, world, rank, barrier, args):
     v = world * TRAIN_BATCH / (ms * 1e-3)
     return {"metric": "rays/sec (train step: fwd+bwd+Adam, coarse64+fine128)", "value": v, "unit": "rays/s",
             "ms_per_step": ms, "rays_per_step_per_gpu": TRAIN_BATCH, "steps": steps,
-            "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "dtype": "bf16" if args.precision in ("bf16", "fp16") else "f32",
             "note": "fused tcgen05 forward with TMA-stored bf16 stash + fused tcgen05 backward-data chain + one grouped split-K dW launch per pass "
                     "+ fused Adam; forward/loss/backward replayed as one CUDA graph; host batches, H2D inside the timed region; one SUM all-reduce of the 2.4 MB gradient "
                     "per step when N>1",
@@ -427,7 +429,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "tc32", "fp32"])
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

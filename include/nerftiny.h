@@ -39,8 +39,12 @@ extern "C" {
 #define NT_ERR_UNSUPPORTED (-5)
 
 /* arithmetic of the MLP contraction */
-#define NT_PREC_FP32 0 /* fp32 FFMA on CUDA cores, layer-major; the 1e-3 "fp32 mode"   */
-#define NT_PREC_BF16 2 /* bf16 operands, fp32 accumulate, tcgen05/TMEM fused kernel     */
+#define NT_PREC_FP32 0 /* fp32 FFMA on CUDA cores, layer-major: the reference arithmetic, forward + backward        */
+#define NT_PREC_TC32 1 /* fp32-tolerance mode on the tensor cores: every operand split into two fp16 (hi + 2^-12 lo), */
+                       /* 3 tcgen05 MMAs per product into two TMEM accumulators; rendering (forward) only            */
+#define NT_PREC_BF16 2 /* bf16 operands, fp32 accumulate, tcgen05/TMEM fused kernels: forward + backward (training)   */
+#define NT_PREC_FP16 3 /* fp16 operands (saturating), fp32 accumulate: same kernels and speed as BF16 with 8x smaller */
+                       /* operand rounding (the network's activations are bounded); rendering (forward) only          */
 
 #define NT_N_LAYERS 12
 #define NT_N_PARAMS 593924
@@ -65,10 +69,12 @@ int nt_layer_table(nt_layer_desc out[NT_N_LAYERS]);
  * the gradient path t_fine -> cdf/weights -> coarse sigma that the reference keeps (nerf.py:255-259).  The fp32
  * gradient along that path is ill-conditioned; the switch lets tests compare the well-conditioned
  * part of the gradient tightly.
- * NT_OPT_MLP_TC_VERSION (default 0 = 7 for rendering; training always 5): schedule of the fused bf16 encode+MLP kernel — 5 tile pair in lock-step,
- * 6 staggered tiles + 2-CTA cluster weight multicast, 7 staggered tiles + tcgen05 cta_group::2. */
+ * NT_OPT_MLP_TC_VERSION (default 0 = 7 for rendering; training always 5): schedule of the fused 16-bit encode+MLP kernel —
+ * 5 tile pair in lock-step, 7 staggered tiles + tcgen05 cta_group::2.
+ * NT_OPT_LAST_DELTA: `last` of render_rays (nerf.py:286, :311; default 1e-4), passed as the BIT PATTERN of the float. */
 #define NT_OPT_DETACH_T_FINE 1
 #define NT_OPT_MLP_TC_VERSION 2
+#define NT_OPT_LAST_DELTA 3
 int nt_set_option(nt_ctx* ctx, int key, int value);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t nt_launch_count(const nt_ctx* ctx);
@@ -100,6 +106,22 @@ int nt_network_forward(nt_ctx* ctx, int64_t total, const float* enc_point, const
  * (multi-GPU shards pass the globally reduced flag).  t_coarse dev [N,Nc]. */
 int nt_sample_coarse(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, int any_step_zero,
                      float* t_coarse, void* stream);
+
+/* ---- batch-global quantities of a ray-SHARDED launch -------------------------------
+ * The reference derives two numbers from the whole batch: numpy's linspace switches formula for EVERY ray when any ray
+ * has a zero step (nerf.py:288) and resample uses t_coarse[0,1] - t_coarse[0,0] of the batch's FIRST ray for all rays
+ * (nerf.py:234).  A shard computes them without a host round trip:
+ *   nt_shard_globals_local   out4 dev float[4] = { flag, delta0 if flag == 0, delta0 if flag == 1, 0 } of THIS shard
+ *                            (flag = 1.0 if any local ray has a zero step; the delta0 candidates come from the shard's ray 0
+ *                            when first_shard != 0 and are -inf otherwise);
+ *   [caller]                 element-wise MAX all-reduce of the 4 floats over the ranks (NCCL, 16 bytes);
+ *   nt_shard_globals_resolve g4 -> g4[0] = delta0 (the candidate the global flag selects), g4[1] = flag.
+ * nt_render_forward then takes any_step_zero = NT_ANY_STEP_ZERO_DEVICE with delta0 = g4 (it reads the flag at
+ * delta0[1]), and nt_render_backward / nt_sample_pdf* take delta0 = g4 as before. */
+#define NT_ANY_STEP_ZERO_DEVICE (-2)
+int nt_shard_globals_local(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, int first_shard,
+                           float* out4, void* stream);
+int nt_shard_globals_resolve(nt_ctx* ctx, float* g4, void* stream);
 
 /* ---- encode + MLP: net_out nerf.py:200-219 = sample positions, Encoder.forward
  *      nerf.py:135-167, Network.forward nerf.py:101-124 -----------------------------------

@@ -14,7 +14,13 @@ LIB_PATH = os.path.join(HERE, "libnerftiny.so")
 NT_OK = 0
 NT_ERR_RANGE = -3
 PREC_FP32 = 0
+PREC_TC32 = 1
 PREC_BF16 = 2
+PREC_FP16 = 3
+ANY_STEP_ZERO_DEVICE = -2
+OPT_DETACH_T_FINE = 1
+OPT_MLP_TC_VERSION = 2
+OPT_LAST_DELTA = 3
 N_PARAMS = 593924
 N_LAYERS = 12
 
@@ -40,6 +46,8 @@ SIGNATURES = {
     "nt_encode": (i32, [vp, i64, vp, vp, vp, vp, vp]),
     "nt_network_forward": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, sz, vp]),
     "nt_sample_coarse": (i32, [vp, i64, vp, vp, i32, vp, vp]),
+    "nt_shard_globals_local": (i32, [vp, i64, vp, vp, i32, vp, vp]),
+    "nt_shard_globals_resolve": (i32, [vp, vp, vp]),
     "nt_mlp_workspace_bytes": (sz, [vp, i32, i64, i32, i32]),
     "nt_packed_weight_bytes": (sz, [vp, i32]),
     "nt_pack_weights": (i32, [vp, i32, vp, vp, vp]),

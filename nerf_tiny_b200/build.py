@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnerftiny.so")
-SOURCES = ["api.cu", "geom.cu", "composite.cu", "composite_fine_fwd.cu", "sample_pdf.cu", "gemm_f32.cu", "mlp_f32.cu", "mlp_tc.cu", "gemm_tc.cu", "bwd_tc.cu", "train_bf16.cu", "adam.cu"]
+SOURCES = ["api.cu", "geom.cu", "composite.cu", "composite_fine_fwd.cu", "sample_pdf.cu", "gemm_f32.cu", "mlp_f32.cu", "mlp_tc.cu", "mlp_tc32.cu", "gemm_tc.cu", "bwd_tc.cu", "train_bf16.cu", "adam.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -41,6 +41,7 @@ __global__ void adam_kernel(int64_t count, float* __restrict__ p, const float* _
 
 extern "C" int nt_adam_step(nt_ctx* ctx, int64_t count, float* params, const float* grads, float* m, float* v, float lr,
                             float beta1, float beta2, float eps, int64_t step, float grad_scale, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && params && grads && m && v, "null pointer");
   NT_REQUIRE(step >= 1, "step is 1-based");
   NT_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "buffers must be 16B aligned");
@@ -115,6 +116,7 @@ __global__ void adam_allreduce_kernel(int64_t count, float* __restrict__ p, Peer
 extern "C" int nt_adam_step_allreduce(nt_ctx* ctx, int64_t count, float* params, const float* const* rank_grads,
                                       int n_ranks, float* m, float* v, float lr, float beta1, float beta2, float eps,
                                       int64_t step, float grad_scale, float* grad_sum_out, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && params && rank_grads && m && v, "null pointer");
   NT_REQUIRE(n_ranks >= 1 && n_ranks <= 8, "1..8 ranks");
   NT_REQUIRE(step >= 1, "step is 1-based");

@@ -42,7 +42,9 @@ extern "C" int nt_create(nt_ctx** out, int device, int n_coarse, int n_fine) {
     nt_set_error("no CUDA device %d (found %d); libnerftiny has no CPU fallback", device, count);
     return NT_ERR_CUDA;
   }
-  NT_CUDA(cudaSetDevice(device));
+  nt_ctx probe;
+  probe.device = device;
+  NT_ENTER(&probe);  // allocate the status flags on `device`; the caller's current device is restored on return
   cudaDeviceProp prop;
   NT_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) {
@@ -58,6 +60,8 @@ extern "C" int nt_create(nt_ctx** out, int device, int n_coarse, int n_fine) {
   c->launches = 0;
   c->opt_detach_t_fine = 0;
   c->opt_tc_version = 0;
+  c->attr_done = 0;
+  c->last_delta = 1e-4f;
   c->d_flags = nullptr;
   if (cudaMalloc(&c->d_flags, 4 * sizeof(int)) != cudaSuccess || cudaMemset(c->d_flags, 0, 4 * sizeof(int)) != cudaSuccess) {
     nt_set_error("cudaMalloc of the status flags failed");
@@ -70,6 +74,7 @@ extern "C" int nt_create(nt_ctx** out, int device, int n_coarse, int n_fine) {
 
 extern "C" void nt_destroy(nt_ctx* ctx) {
   if (!ctx) return;
+  NT_ENTER(ctx);
   if (ctx->d_flags) cudaFree(ctx->d_flags);
   delete ctx;
 }
@@ -83,8 +88,15 @@ extern "C" int nt_set_option(nt_ctx* ctx, int key, int value) {
     return NT_OK;
   }
   if (key == NT_OPT_MLP_TC_VERSION) {
-    NT_REQUIRE(value == 0 || (value >= 5 && value <= 7), "mlp_tc version must be 0 (default), 5, 6 or 7");
+    NT_REQUIRE(value == 0 || value == 5 || value == 7, "mlp_tc version must be 0 (default), 5 or 7");
     ctx->opt_tc_version = value;
+    return NT_OK;
+  }
+  if (key == NT_OPT_LAST_DELTA) {
+    float f;
+    memcpy(&f, &value, sizeof(f));
+    NT_REQUIRE(f == f && f >= 0.f, "last delta must be a non-negative float (passed as its bit pattern)");
+    ctx->last_delta = f;
     return NT_OK;
   }
   nt_set_error("unknown option %d", key);
@@ -92,26 +104,36 @@ extern "C" int nt_set_option(nt_ctx* ctx, int key, int value) {
 }
 
 // ---- precision dispatch ------------------------------------------------------------------------
+static bool is_tc16(int precision) { return precision == NT_PREC_BF16 || precision == NT_PREC_FP16; }
+static bool known_precision(int precision) {
+  return precision == NT_PREC_FP32 || precision == NT_PREC_TC32 || is_tc16(precision);
+}
+
 extern "C" size_t nt_mlp_workspace_bytes(nt_ctx* ctx, int precision, int64_t n, int p, int train) {
   (void)ctx;
   if (precision == NT_PREC_FP32) return nt_mlp_f32_workspace_bytes(n, p, train);
   if (precision == NT_PREC_BF16) return train ? nt_mlp_bf16_train_workspace_bytes(n, p) : 256;
+  if (precision == NT_PREC_FP16 || precision == NT_PREC_TC32) return train ? 0 : 256;  // rendering modes
   return 0;
 }
 extern "C" size_t nt_packed_weight_bytes(nt_ctx* ctx, int precision) {
   (void)ctx;
-  return precision == NT_PREC_BF16 ? nt_mlp_tc_packed_bytes() : 0;
+  if (is_tc16(precision)) return nt_mlp_tc_packed_bytes();
+  return precision == NT_PREC_TC32 ? nt_mlp_tc32_packed_bytes() : 0;
 }
 extern "C" int nt_pack_weights(nt_ctx* ctx, int precision, const float* params, void* packed, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && params, "null pointer");
   if (precision == NT_PREC_FP32) return NT_OK;
-  NT_REQUIRE(precision == NT_PREC_BF16 && packed, "bad precision / null packed buffer");
-  return nt_mlp_tc_pack(ctx, params, packed, (cudaStream_t)stream);
+  NT_REQUIRE(known_precision(precision) && packed, "bad precision / null packed buffer");
+  const int mode = precision == NT_PREC_BF16 ? 0 : (precision == NT_PREC_FP16 ? 1 : 2);
+  return nt_mlp_tc_pack(ctx, params, packed, mode, (cudaStream_t)stream);
 }
 
 extern "C" int nt_mlp_forward(nt_ctx* ctx, int precision, int64_t n, int p, const float* t, const float* rays,
                               const float* dir_enc, const float* params, const void* packed, float* rgb, float* sigma,
                               void* ws, size_t ws_bytes, int train, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && t && rays && dir_enc && params && rgb && sigma, "null pointer");
   NT_REQUIRE(p > 0 && n >= 0, "bad shape");
   if (n == 0) return NT_OK;
@@ -119,22 +141,29 @@ extern "C" int nt_mlp_forward(nt_ctx* ctx, int precision, int64_t n, int p, cons
     NT_REQUIRE(ws, "fp32 MLP needs a workspace");
     return nt_mlp_f32_forward(ctx, n, p, t, rays, dir_enc, params, rgb, sigma, ws, ws_bytes, train, (cudaStream_t)stream);
   }
-  if (precision == NT_PREC_BF16) {
-    NT_REQUIRE(packed, "NT_PREC_BF16 needs packed weights (nt_pack_weights)");
-    if (train) {  // fused tcgen05 forward + bf16 activation stash for the tensor-core backward
-      NT_REQUIRE(ws, "bf16 training needs a workspace");
-      return nt_mlp_bf16_train_forward(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, ws, ws_bytes,
-                                       (cudaStream_t)stream);
-    }
-    return nt_mlp_tc_forward(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, (cudaStream_t)stream);
+  if (!known_precision(precision)) {
+    nt_set_error("unknown precision %d", precision);
+    return NT_ERR_UNSUPPORTED;
   }
-  nt_set_error("unknown precision %d", precision);
-  return NT_ERR_UNSUPPORTED;
+  NT_REQUIRE(packed, "the tensor-core precisions need packed weights (nt_pack_weights with the same precision)");
+  if (train) {  // fused tcgen05 forward + bf16 activation stash for the tensor-core backward
+    if (precision != NT_PREC_BF16) {
+      nt_set_error("NT_PREC_FP16 / NT_PREC_TC32 are rendering modes; train with NT_PREC_BF16 or NT_PREC_FP32");
+      return NT_ERR_UNSUPPORTED;
+    }
+    NT_REQUIRE(ws, "bf16 training needs a workspace");
+    return nt_mlp_bf16_train_forward(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, ws, ws_bytes,
+                                     (cudaStream_t)stream);
+  }
+  if (precision == NT_PREC_TC32) return nt_mlp_tc32_forward(ctx, n, p, t, rays, dir_enc, packed, rgb, sigma, (cudaStream_t)stream);
+  return nt_mlp_tc_forward(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, precision == NT_PREC_FP16 ? 1 : 0,
+                           (cudaStream_t)stream);
 }
 
 extern "C" int nt_mlp_backward(nt_ctx* ctx, int precision, int64_t n, int p, const float* t, const float* rays,
                                const float* dir_enc, const float* params, const void* packed, const float* g_rgb,
                                const float* g_sigma, float* grads, float* g_t, void* ws, size_t ws_bytes, void* stream) {
+  NT_ENTER(ctx);
   (void)dir_enc;
   (void)packed;
   NT_REQUIRE(ctx && t && rays && params && g_rgb && g_sigma && grads && ws, "null pointer");
@@ -213,6 +242,7 @@ extern "C" int nt_render_forward(nt_ctx* ctx, int precision, int64_t n, const in
                                  const float* far_, const float* params, const void* packed, int any_step_zero,
                                  const float* delta0, float* c_coarse, float* c_fine, void* ws, size_t ws_bytes,
                                  int train, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && row && col && c2w && kinv && near_ && far_ && params && c_coarse && c_fine && ws, "null pointer");
   if (n <= 0) return NT_OK;
   RenderWs w = carve_render(ctx, ws, precision, n, train);
@@ -222,14 +252,15 @@ extern "C" int nt_render_forward(nt_ctx* ctx, int precision, int64_t n, const in
   }
   const int nc = ctx->n_coarse, nf = ctx->n_fine;
   NT_TRY(nt_raygen(ctx, n, row, col, c2w, c2w_stride, kinv, w.rays, nullptr, w.dir_enc, stream));
-  NT_TRY(nt_sample_coarse(ctx, n, near_, far_, any_step_zero, w.t_c, stream));                         // nerf.py:288
+  NT_TRY(nt_launch_sample_coarse(ctx, n, near_, far_, any_step_zero, delta0 ? delta0 + 1 : nullptr, w.t_c,
+                                 (cudaStream_t)stream));                                                // nerf.py:288
   NT_TRY(nt_mlp_forward(ctx, precision, n, nc, w.t_c, w.rays, w.dir_enc, params, packed, w.rgb_c, w.sig_c, w.mlp_c,
                         w.mlp_c_bytes, train, stream));                                                // nerf.py:289
   NT_TRY(nt_composite_coarse(ctx, n, near_, far_, w.rgb_c, w.sig_c, w.w_c, c_coarse, stream));         // nerf.py:293-295, 320
   NT_TRY(nt_sample_pdf(ctx, n, w.t_c, w.w_c, delta0, w.t_f, nullptr, stream));                         // nerf.py:298
   NT_TRY(nt_mlp_forward(ctx, precision, n, nf, w.t_f, w.rays, w.dir_enc, params, packed, w.rgb_f, w.sig_f, w.mlp_f,
                         w.mlp_f_bytes, train, stream));                                                // nerf.py:299
-  NT_TRY(nt_composite_fine(ctx, n, w.t_c, w.rgb_c, w.sig_c, w.t_f, w.rgb_f, w.sig_f, 1e-4f, c_fine, nullptr,
+  NT_TRY(nt_composite_fine(ctx, n, w.t_c, w.rgb_c, w.sig_c, w.t_f, w.rgb_f, w.sig_f, ctx->last_delta, c_fine, nullptr,
                            train ? w.perm : nullptr, stream));                                         // nerf.py:302-321
   return NT_OK;
 }
@@ -238,6 +269,7 @@ extern "C" int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const f
                                   const float* params, const void* packed, const float* delta0,
                                   const float* g_c_coarse, const float* g_c_fine, float* grads, void* ws,
                                   size_t ws_bytes, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && near_ && far_ && params && g_c_coarse && g_c_fine && grads && ws, "null pointer");
   if (n <= 0) return NT_OK;
   RenderWs w = carve_render(ctx, ws, precision, n, 1);
@@ -247,7 +279,7 @@ extern "C" int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const f
   }
   const int nc = ctx->n_coarse, nf = ctx->n_fine;
   // C_fine <- sort/composite (B.2, B.3)
-  NT_TRY(nt_composite_fine_backward(ctx, n, w.t_c, w.rgb_c, w.sig_c, w.t_f, w.rgb_f, w.sig_f, 1e-4f, w.perm, g_c_fine,
+  NT_TRY(nt_composite_fine_backward(ctx, n, w.t_c, w.rgb_c, w.sig_c, w.t_f, w.rgb_f, w.sig_f, ctx->last_delta, w.perm, g_c_fine,
                                     w.g_rgb_c, w.g_sig_c, w.g_rgb_f, w.g_sig_f, w.g_t_f, stream));
   // fine MLP: dW + input gradient down to t_fine (B.4, B.6, B.7)
   const bool detach = ctx->opt_detach_t_fine != 0;
@@ -286,6 +318,7 @@ static int nt_launch_axpy(nt_ctx* ctx, int64_t n, const float* x, float* y, cuda
 // The workspace is that of nt_mlp_workspace_bytes(ctx, NT_PREC_FP32, total, 1, 0).
 extern "C" int nt_network_forward(nt_ctx* ctx, int64_t total, const float* enc_point, const float* enc_dir,
                                   const float* params, float* rgb, float* sigma, void* ws, size_t ws_bytes, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx, "null ctx");
   if (total <= 0) return NT_OK;
   NT_REQUIRE(enc_point && enc_dir && params && rgb && sigma && ws, "null pointer");
@@ -297,6 +330,7 @@ extern "C" int nt_network_forward(nt_ctx* ctx, int64_t total, const float* enc_p
 extern "C" int nt_mlp_forward_debug(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays,
                                     const float* dir_enc, const float* params, const void* packed, float* rgb,
                                     float* sigma, float* dbg, int layer, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && t && rays && dir_enc && params && packed && rgb && sigma && dbg, "null pointer");
   if (n <= 0) return NT_OK;
   return nt_mlp_tc_forward_dbg(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, dbg, layer, (cudaStream_t)stream);
@@ -306,6 +340,7 @@ extern "C" int nt_mlp_forward_debug(nt_ctx* ctx, int64_t n, int p, const float* 
 // 1: A [K][M], B [K][N].  out_f32 = 0: C bf16 [M][ldc]; 1: fp32 atomically accumulated into C.
 extern "C" int nt_gemm_bf16_debug(nt_ctx* ctx, int mn_major, int m, int n, int k, const void* a, int lda, const void* b,
                                   int ldb, void* c, int ldc, int out_f32, const void* mask, int ldmask, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && a && b && c, "null pointer");
   GemmTcEpi e;
   memset(&e, 0, sizeof(e));

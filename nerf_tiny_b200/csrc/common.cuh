@@ -11,6 +11,7 @@
 #define NT_WARP 32
 #define NT_MAX_COARSE 64
 #define NT_MAX_FINE 128
+#define NT_MAX_DEVICES 64
 
 struct nt_ctx {
   int device;
@@ -20,9 +21,29 @@ struct nt_ctx {
   int64_t launches;
   int opt_detach_t_fine;
   int opt_tc_version;
+  float last_delta;    // delta of the last merged sample (render_rays `last`, nerf.py:286, :311); default 1e-4
+  unsigned attr_done;  // NT_ATTR_*: cudaFuncSetAttribute is per DEVICE, so the "already opted in" bits live in the ctx
+};
+enum {
+  NT_ATTR_MLP_TC5 = 1u << 0, NT_ATTR_MLP_TC7 = 1u << 1, NT_ATTR_MLP_TC32 = 1u << 2, NT_ATTR_GEMM_TC = 1u << 3,
+  NT_ATTR_DW_GROUPED = 1u << 4, NT_ATTR_DW_GEMM = 1u << 5, NT_ATTR_BWD_TC = 1u << 6
 };
 
 void nt_set_error(const char* fmt, ...);
+
+// Every launching entry point runs on the context's device, whatever device the caller has current, and leaves the
+// caller's current device untouched (nt_create does not switch it either).
+struct NtDeviceGuard {
+  int prev;
+  bool changed;
+  explicit NtDeviceGuard(const nt_ctx* ctx) : prev(-1), changed(false) {
+    if (ctx && cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device) changed = cudaSetDevice(ctx->device) == cudaSuccess;
+  }
+  ~NtDeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
+#define NT_ENTER(ctx) NtDeviceGuard nt_guard__(ctx)
 
 #define NT_CUDA(call)                                                                      \
   do {                                                                                     \
@@ -79,6 +100,8 @@ static inline LayerTable nt_layers() {
 
 // ---- internal launchers (one per .cu) ---------------------------------------------------------
 // geom.cu
+int nt_launch_sample_coarse(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, int any_step_zero,
+                            const float* flag_dev, float* t_coarse, cudaStream_t st);
 int nt_launch_encode_points(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, float* enc, int ld_enc,
                             cudaStream_t st);
 int nt_launch_expand_dir_enc(nt_ctx* ctx, int64_t n, int p, const float* dir_enc, float* out, int ld, cudaStream_t st);
@@ -122,12 +145,17 @@ int nt_mlp_f32_backward(nt_ctx* ctx, int64_t n, int p, const float* t, const flo
 
 // mlp_tc.cu (tcgen05 / TMEM fused encode+MLP, bf16 operands)
 size_t nt_mlp_tc_packed_bytes();
-int nt_mlp_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t st);
+int nt_mlp_tc_pack(nt_ctx* ctx, const float* params, void* packed, int mode /*0 bf16, 1 fp16, 2 split fp16 (tc32)*/,
+                   cudaStream_t st);
 int nt_mlp_tc_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
-                      const float* params, const void* packed, float* rgb, float* sigma, cudaStream_t st);
+                      const float* params, const void* packed, float* rgb, float* sigma, int fp16, cudaStream_t st);
 int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                           const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int dbg_layer,
                           cudaStream_t st);
+// mlp_tc32.cu (NT_PREC_TC32: 3-pass split-fp16 tcgen05 forward with two TMEM accumulators)
+size_t nt_mlp_tc32_packed_bytes();
+int nt_mlp_tc32_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
+                        const void* packed, float* rgb, float* sigma, cudaStream_t st);
 // composite_fine_fwd.cu
 int nt_launch_composite_fine_fwd(nt_ctx* ctx, int64_t n, const float* t_c, const float* rgb_c, const float* sigma_c,
                                  const float* t_f, const float* rgb_f, const float* sigma_f, float last, float* c_out,

@@ -383,6 +383,7 @@ __global__ void ray_loss_kernel(int64_t n3, const float* __restrict__ cc, const 
 // ---------------------------------------------------------------------------------------------
 extern "C" int nt_composite_coarse(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, const float* rgb,
                                    const float* sigma, float* weights, float* c_out, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && near_ && far_ && rgb && sigma && weights && c_out, "null pointer");
   NT_REQUIRE(ctx->n_coarse == 64, "coarse compositing is built for Nc=64");
   if (n <= 0) return NT_OK;
@@ -406,6 +407,7 @@ extern "C" int nt_composite_coarse(nt_ctx* ctx, int64_t n, const float* near_, c
 
 extern "C" int nt_get_density(nt_ctx* ctx, int64_t n, int p, const float* delta, const float* sigma, float* weights,
                               void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx, "null ctx");
   NT_REQUIRE(p > 0 && p <= 256 && p % 32 == 0, "get_density: samples per ray must be a multiple of 32, at most 256");
   if (n <= 0) return NT_OK;
@@ -418,6 +420,7 @@ extern "C" int nt_get_density(nt_ctx* ctx, int64_t n, int p, const float* delta,
 
 extern "C" int nt_color_cum(nt_ctx* ctx, int64_t n, int p, const float* weights, const float* rgb, float* c_out,
                             void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx, "null ctx");
   NT_REQUIRE(p > 0 && p <= 256 && p % 32 == 0, "color_cum: samples per ray must be a multiple of 32, at most 256");
   if (n <= 0) return NT_OK;
@@ -431,6 +434,7 @@ extern "C" int nt_color_cum(nt_ctx* ctx, int64_t n, int p, const float* weights,
 extern "C" int nt_composite_coarse_backward(nt_ctx* ctx, int64_t n, const float* near_, const float* far_,
                                             const float* rgb, const float* sigma, const float* g_c,
                                             const float* g_w_ext, float* g_rgb, float* g_sigma, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && near_ && far_ && rgb && sigma && g_c && g_rgb && g_sigma, "null pointer");
   NT_REQUIRE(ctx->n_coarse == 64, "coarse compositing is built for Nc=64");
   if (n <= 0) return NT_OK;
@@ -443,6 +447,7 @@ extern "C" int nt_composite_coarse_backward(nt_ctx* ctx, int64_t n, const float*
 extern "C" int nt_composite_fine(nt_ctx* ctx, int64_t n, const float* t_c, const float* rgb_c, const float* sigma_c,
                                  const float* t_f, const float* rgb_f, const float* sigma_f, float last, float* c_out,
                                  float* weights, uint8_t* perm, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && t_c && rgb_c && sigma_c && t_f && rgb_f && sigma_f && c_out, "null pointer");
   NT_REQUIRE(ctx->n_coarse + ctx->n_fine == 192, "fine compositing is built for Nc+Nf=192");
   if (n <= 0) return NT_OK;
@@ -458,6 +463,7 @@ extern "C" int nt_composite_fine_backward(nt_ctx* ctx, int64_t n, const float* t
                                           const float* sigma_f, float last, const uint8_t* perm, const float* g_c,
                                           float* g_rgb_c, float* g_sigma_c, float* g_rgb_f, float* g_sigma_f,
                                           float* g_t_f, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && t_c && rgb_c && sigma_c && t_f && rgb_f && sigma_f && perm && g_c, "null pointer");
   NT_REQUIRE(g_rgb_c && g_sigma_c && g_rgb_f && g_sigma_f && g_t_f, "null output pointer");
   NT_REQUIRE(ctx->n_coarse + ctx->n_fine == 192, "fine compositing is built for Nc+Nf=192");
@@ -472,6 +478,7 @@ extern "C" int nt_composite_fine_backward(nt_ctx* ctx, int64_t n, const float* t
 
 extern "C" int nt_ray_loss(nt_ctx* ctx, int64_t n, const float* c_coarse, const float* c_fine, const float* c_true,
                            float* loss, float* g_cc, float* g_cf, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && c_coarse && c_fine && c_true, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (loss) NT_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));

@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -41,92 +42,13 @@ struct GemmTcArgs {
   float* colsum;        // optional [N]: += column sums of the stored matrix (bias gradient of the layer below)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  long long t0 = 0;
-  int spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins == 1024) t0 = clock64();
-    if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();  // never hang the GPU
-  }
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-
-// K-major SW128 descriptor (8-row groups 1024 B apart) / MN-major SW128 descriptor (64-element MN blocks `lbo` bytes
-// apart, 8-row K groups 1024 B apart) — cute::UMMA::SmemDescriptor bit layout
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__host__ __device__ constexpr uint32_t idesc_bf16(int n, bool mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (1u << 15) | (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(BM >> 4) << 24);
-}
+// PTX wrappers: tc_ptx.cuh
+using namespace tcptx;
+__host__ __device__ constexpr uint32_t idesc_bf16(int n, bool mn_major) { return idesc_f16kind(BM, n, true, mn_major); }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
+  umma_f16(d_tmem, adesc, bdesc, idesc, acc);
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :
-               : "memory");
-}
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) { return pack_bf16(lo, hi); }
 
 // fp32 atomic accumulation of 32 consecutive values: 16-byte vector reductions on the aligned middle, scalar atomics on
 // the (at most 3 + 3) unaligned head/tail elements — the flat parameter layout is only 4-byte aligned after the
@@ -700,10 +622,10 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
 template <int BN, bool MN>
 int launch(nt_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const GemmTcArgs& g, cudaStream_t st) {
   constexpr int smem = NSTAGE * A_STAGE_BYTES + NSTAGE * BN * 128 + 128;
-  static bool set = false;
-  if (!set) {
+  static bool set[NT_MAX_DEVICES] = {};  // the opt-in is per device (and per template instantiation)
+  if (!set[ctx->device]) {
     NT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = true;
+    set[ctx->device] = true;
   }
   const int items = ((g.M + BM - 1) / BM) * g.split_k;
   const int grid = items < ctx->sm_count ? items : ctx->sm_count;
@@ -796,10 +718,10 @@ int nt_launch_dw_gemm(nt_ctx* ctx, int S, const void* G, int ldg, int m_valid, c
 #define DW_LAUNCH(BN_)                                                                                              \
   {                                                                                                                 \
     constexpr int smem = DW_STAGES * (DW_A_BYTES + BN_ * 128) + 128;                                                \
-    static bool set = false;                                                                                        \
-    if (!set) {                                                                                                     \
+    static bool set[NT_MAX_DEVICES] = {};                                                                           \
+    if (!set[ctx->device]) {                                                                                        \
       NT_CUDA(cudaFuncSetAttribute(dw_gemm_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
-      set = true;                                                                                                   \
+      set[ctx->device] = true;                                                                                      \
     }                                                                                                               \
     dw_gemm_kernel<BN_><<<ctas, GEMM_THREADS, smem, st>>>(ma, mb, g);                                               \
   }
@@ -864,10 +786,9 @@ int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st) {
   }
   g.cta_begin[g.n_problems] = begin;
   constexpr int smem = DW_STAGES * (DW_A_BYTES + 256 * 128) + 128;
-  static bool set = false;
-  if (!set) {
+  if (!(ctx->attr_done & NT_ATTR_DW_GROUPED)) {
     NT_CUDA(cudaFuncSetAttribute(dw_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = true;
+    ctx->attr_done |= NT_ATTR_DW_GROUPED;
   }
   dw_grouped_kernel<<<begin, GEMM_THREADS, smem, st>>>(g);
   NT_LAUNCH_CHECK(ctx);

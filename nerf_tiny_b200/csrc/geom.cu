@@ -73,8 +73,41 @@ __global__ void step_zero_flag_kernel(int64_t n, const float* __restrict__ near_
   if (z && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
+// Batch-global quantities of a ray-sharded launch: out[0] = 1 if any LOCAL ray has a zero linspace step
+// (max-accumulated: the caller zeroes out[0] first), out[1] / out[2] = t_coarse[0,1] - t_coarse[0,0] of this shard's ray 0
+// as np.linspace produces it when the global flag is 0 / 1 (nerf.py:234, :288), or -inf when this is not the first shard.
+// An element-wise MAX over the ranks' vectors is then the global triple.
+__global__ void shard_globals_local_kernel(int64_t n, const float* __restrict__ near_, const float* __restrict__ far_,
+                                           int nc, int first_shard, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int z = 0;
+  if (i < n) z = (__fdiv_rn(__fsub_rn(far_[i], near_[i]), (float)(nc - 1)) == 0.f);
+  z = __any_sync(0xffffffffu, z);
+  if (z && (threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(1.0f));  // 0.0f / 1.0f order as ints
+  if (i == 0) {
+    float d0 = -INFINITY, d1 = -INFINITY;
+    if (first_shard) {
+      const float a = near_[0], b = far_[0], div = (float)(nc - 1), delta = __fsub_rn(b, a);
+      const float t1a = nc == 2 ? b : __fadd_rn(__fmul_rn(1.f, __fdiv_rn(delta, div)), a);
+      const float t1b = nc == 2 ? b : __fadd_rn(__fmul_rn(__fdiv_rn(1.f, div), delta), a);
+      d0 = __fsub_rn(t1a, a);  // t_coarse[0,0] == near in both branches
+      d1 = __fsub_rn(t1b, a);
+    }
+    out[1] = d0;
+    out[2] = d1;
+    out[3] = 0.f;
+  }
+}
+__global__ void shard_globals_resolve_kernel(float* __restrict__ g) {
+  const float flag = g[0] != 0.f ? 1.f : 0.f;
+  const float d = flag != 0.f ? g[2] : g[1];
+  g[0] = d;     // delta0, where nt_sample_pdf / nt_render_* read it
+  g[1] = flag;  // any_step_zero, read by the coarse sampler when any_step_zero == NT_ANY_STEP_ZERO_DEVICE
+}
+
 __global__ void sample_coarse_kernel(int64_t n, const float* __restrict__ near_, const float* __restrict__ far_,
-                                     int nc, int forced, const int* __restrict__ flag, float* __restrict__ t) {
+                                     int nc, int forced, const int* __restrict__ flag, const float* __restrict__ flag_f,
+                                     float* __restrict__ t) {
   int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n * nc) return;
   int64_t r = gid / nc;
@@ -82,7 +115,7 @@ __global__ void sample_coarse_kernel(int64_t n, const float* __restrict__ near_,
   const float a = near_[r], b = far_[r];
   const float div = (float)(nc - 1);
   const float delta = __fsub_rn(b, a);
-  const int zero = forced >= 0 ? forced : *flag;
+  const int zero = forced >= 0 ? forced : (flag_f ? (*flag_f != 0.f) : *flag);
   float y;
   if (zero)
     y = __fadd_rn(__fmul_rn(__fdiv_rn((float)i, div), delta), a);
@@ -213,6 +246,7 @@ __global__ void encode_backward_kernel(int64_t total, int p, const float* __rest
 // ---------------------------------------------------------------------------------------------
 extern "C" int nt_raygen(nt_ctx* ctx, int64_t n, const int64_t* row, const int64_t* col, const float* c2w,
                          int c2w_stride, const float* kinv, float* rays, float* dir_wrd, float* dir_enc, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && row && col && c2w && kinv && rays, "null pointer");
   NT_REQUIRE(c2w_stride == 16 || c2w_stride == 12 || c2w_stride == 17, "c2w_stride must be 12, 16 or 17");
   if (n <= 0) return NT_OK;
@@ -222,20 +256,53 @@ extern "C" int nt_raygen(nt_ctx* ctx, int64_t n, const int64_t* row, const int64
   return NT_OK;
 }
 
-extern "C" int nt_sample_coarse(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, int any_step_zero,
-                                float* t_coarse, void* stream) {
-  if (n <= 0) return NT_OK;
-  NT_REQUIRE(ctx && near_ && far_ && t_coarse, "null pointer");
-  cudaStream_t st = (cudaStream_t)stream;
+int nt_launch_sample_coarse(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, int any_step_zero,
+                            const float* flag_dev, float* t_coarse, cudaStream_t st) {
   const int nc = ctx->n_coarse;
-  if (any_step_zero < 0) {
-    NT_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), st));
-    step_zero_flag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, near_, far_, nc, ctx->d_flags);
-    NT_LAUNCH_CHECK(ctx);
+  if (any_step_zero == NT_ANY_STEP_ZERO_DEVICE) {
+    NT_REQUIRE(flag_dev, "NT_ANY_STEP_ZERO_DEVICE needs the device-resident globals (nt_shard_globals_resolve)");
+  } else {
+    flag_dev = nullptr;
+    if (any_step_zero < 0) {
+      NT_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), st));
+      step_zero_flag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, near_, far_, nc, ctx->d_flags);
+      NT_LAUNCH_CHECK(ctx);
+    }
   }
   int64_t total = n * nc;
-  sample_coarse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, near_, far_, nc, any_step_zero, ctx->d_flags,
-                                                                       t_coarse);
+  sample_coarse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, near_, far_, nc, flag_dev ? -1 : any_step_zero,
+                                                                       ctx->d_flags, flag_dev, t_coarse);
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
+
+extern "C" int nt_sample_coarse(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, int any_step_zero,
+                                float* t_coarse, void* stream) {
+  NT_ENTER(ctx);
+  if (n <= 0) return NT_OK;
+  NT_REQUIRE(ctx && near_ && far_ && t_coarse, "null pointer");
+  NT_REQUIRE(any_step_zero >= -1 && any_step_zero <= 1, "any_step_zero must be -1, 0 or 1 here");
+  return nt_launch_sample_coarse(ctx, n, near_, far_, any_step_zero, nullptr, t_coarse, (cudaStream_t)stream);
+}
+
+extern "C" int nt_shard_globals_local(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, int first_shard,
+                                      float* out4, void* stream) {
+  NT_ENTER(ctx);
+  NT_REQUIRE(ctx && out4 && (n == 0 || (near_ && far_)), "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  NT_CUDA(cudaMemsetAsync(out4, 0, 4 * sizeof(float), st));
+  // an empty shard (more ranks than rays) still contributes the neutral element
+  const int64_t threads = n > 0 ? n : 1;
+  shard_globals_local_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, near_, far_, ctx->n_coarse,
+                                                                              (first_shard && n > 0) ? 1 : 0, out4);
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
+
+extern "C" int nt_shard_globals_resolve(nt_ctx* ctx, float* g4, void* stream) {
+  NT_ENTER(ctx);
+  NT_REQUIRE(ctx && g4, "null pointer");
+  shard_globals_resolve_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(g4);
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;
 }
@@ -251,6 +318,7 @@ int nt_launch_encode_points(nt_ctx* ctx, int64_t n, int p, const float* t, const
 
 extern "C" int nt_encode(nt_ctx* ctx, int64_t total, const float* points, const float* dirs, float* gamma_point,
                          float* gamma_dir, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx, "null ctx");
   if (total <= 0) return NT_OK;
   cudaStream_t st = (cudaStream_t)stream;

@@ -15,53 +15,17 @@
 // Skip (nerf.py:109) and view (nerf.py:118) concatenations are extra K-chunks accumulated into the same TMEM tile.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
+#include "mlp_layout.cuh"
 
 namespace {
 
-constexpr int TILE_M = 128;
-constexpr int CHUNK_A_BYTES = TILE_M * 128;      // [128 rows x 64 bf16], one swizzle row per sample
-constexpr int ACT_BYTES = 4 * CHUNK_A_BYTES;     // 256-wide activations
-constexpr int W_STAGE_BYTES = 256 * 128;         // [256 x 64] bf16
-constexpr int N_STAGES = 2;
-constexpr int OFF_ACT = 0;
-constexpr int OFF_ENC = 2 * ACT_BYTES;
-constexpr int OFF_W = OFF_ENC + 2 * CHUNK_A_BYTES;
-constexpr int OFF_BAR = OFF_W + N_STAGES * W_STAGE_BYTES;
-constexpr int AUX_REC_FLOATS = 640;                // per-layer fp32 record: bias[256] | head weights[384]
-constexpr int OFF_AUX = OFF_BAR + 128;             // single-buffered stage for the current layer's record
-constexpr int SMEM_BYTES = OFF_AUX + AUX_REC_FLOATS * 4;
-constexpr int N_MMA_LAYERS = 10;  // L0..L7, point_info, dir_info
-constexpr int N_EPI_WARPS = 16;   // per tile: 4 lane quadrants x 2 column halves
-constexpr int WARP_TMA = 16, WARP_MMA = 17;
-constexpr int N_THREADS = 576;    // 16 epilogue warps + TMA producer + MMA issuer
-
-// barrier slots (8 B each) inside the OFF_BAR block
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = 2, BAR_ACC_FULL = 4, BAR_ACT_READY = 6, BAR_AUX_FULL = 8, BAR_COUNT = 9 };
-
-__host__ __device__ constexpr int layer_chunks(int L) { return L == 0 ? 1 : ((L == 4 || L == 9) ? 5 : 4); }
-__host__ __device__ constexpr int layer_n(int L) { return L == 9 ? 128 : 256; }
-__host__ __device__ constexpr int chunk_bytes(int L) { return layer_n(L) * 128; }
-constexpr int total_packed_bytes() {
-  int b = 0;
-  for (int L = 0; L < N_MMA_LAYERS; ++L) b += layer_chunks(L) * chunk_bytes(L);
-  return b;
-}
-constexpr int PACKED_W_BYTES = total_packed_bytes();  // 1 196 032
-// fp32 side block appended to the packed weights, 16-byte aligned (the flat parameter buffer is not: the
-// 1-wide sigma bias shifts everything after it by one float)
-// one record per tensor-core layer, TMA-copied into shared memory right before the layer's epilogue:
-//   [0,256)  bias (dir_info: 128 biases, then the 3 colour biases at 128..130)
-//   [256,640) head weights: layer 7 -> sigma weights [256] + sigma bias at 512; layer 9 -> colour weights [3][128]
-constexpr int AUX_EXTRA = 256;
-constexpr int AUX_SIG_B = 512;
-constexpr int AUX_COL_B = 128;
-constexpr int AUX_FLOATS = N_MMA_LAYERS * AUX_REC_FLOATS;
-constexpr int PACKED_BYTES = PACKED_W_BYTES + AUX_FLOATS * 4;
-__host__ __device__ constexpr int aux_bytes(int L) { return (L == 7 || L == 9) ? AUX_REC_FLOATS * 4 : 1024; }
+using namespace mlpl;
 
 struct TcParams {
   const float* t;
@@ -92,120 +56,15 @@ struct TcParams {
 
 __constant__ uint32_t c_tc_freq_point[10] = NT_FREQ_POINT_INIT;
 
-// ---------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// PTX wrappers: tc_ptx.cuh (shared with bwd_tc.cu / gemm_tc.cu / mlp_tc32.cu)
+using namespace tcptx;
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  long long t0 = 0;
-  int spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins == 1024) t0 = clock64();
-    if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();  // ~2 s: never hang the GPU
-  }
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
-               "r"(src)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc_512(uint32_t smem_slot) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_slot) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
-}
-
-// SM100 shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
-__host__ __device__ constexpr uint32_t umma_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) { return desc_kmajor(saddr); }
+// instruction descriptor: D=f32, A=B=bf16 (F16 = false) or fp16, both K-major, M=128
+template <bool F16 = false>
+__host__ __device__ constexpr uint32_t umma_idesc(int n) { return idesc_f16kind(TILE_M, n, !F16); }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// asynchronous TMEM -> register load of 32 consecutive fp32 columns of this thread's lane; the registers may only
-// be read after tmem_ld_wait() on the same array (the "+r" operands make that a data dependency for the compiler)
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :
-               : "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // lo -> lower address
-  return r;
-}
-__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  umma_f16(d_tmem, adesc, bdesc, idesc, acc);
 }
 
 // sin/cos for the bf16 path: 2-term Cody-Waite reduction by 2*pi, then the SFU (abs err ~1e-6, far below bf16's 4e-3)
@@ -218,14 +77,6 @@ __device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
   c = __cosf(r);
 }
 
-// per-thread view of the shared-memory operand tiles: row `row` of a [128 x 64] bf16 SW128 tile lives at
-// tile + row*128, its 16-byte chunk j at ((j ^ (row & 7)) << 4)
-struct RowSwz {
-  uint32_t row_off;  // row * 128
-  uint32_t x4;       // (row & 7) << 4
-  __device__ __forceinline__ uint32_t addr(uint32_t tile, int j) const { return tile + row_off + (x4 ^ (uint32_t)(j << 4)); }
-};
-
 enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_COLOUR = 3 };
 
 // diagnostic timeline (debug instantiation only, dbg_layer >= 100): clock64 stamps of block 0's first 4 tile pairs,
@@ -235,43 +86,6 @@ enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_COLOUR = 3 };
     if (DBG && P.dbg_layer >= 100 && blockIdx.x == 0 && pair_local < 4)                                      \
       reinterpret_cast<long long*>(P.dbg)[(pair_local * 10 + L) * 16 + (slot)] = clock64();                  \
   } while (0)
-
-// (d0, d1) = (a0, a1) + (b0, b1) in one packed instruction (sm_100 add.f32x2; same rounding as two add.rn.f32)
-__device__ __forceinline__ void add_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-  asm("{\n\t.reg .b64 pa, pb, pd;\n\t"
-      "mov.b64 pa, {%2, %3};\n\t"
-      "mov.b64 pb, {%4, %5};\n\t"
-      "add.rn.f32x2 pd, pa, pb;\n\t"
-      "mov.b64 {%0, %1}, pd;\n\t}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float lds32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-  return v;
-}
-// single-column TMEM exchange between the two threads that own the same row (warps w and w+8 share a lane quadrant)
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(a)),
-               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
-               : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float& a, float& b, float& c, float& d) {
-  uint32_t r0, r1, r2, r3;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3)::"memory");
-  a = __uint_as_float(r0);
-  b = __uint_as_float(r1);
-  c = __uint_as_float(r2);
-  d = __uint_as_float(r3);
-}
 
 // One layer's epilogue for one thread: the thread owns one sample (= one TMEM lane) and one half of the layer's
 // output columns.  accumulator -> +bias -> activation -> bf16 A operand of the next layer (or the heads).
@@ -628,383 +442,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
   }
 }
 
-// =========================================================================================================
-// v6: tile-STAGGERED schedule on a 2-CTA cluster.
-// The tensor core alternates between the CTA's two tiles one whole layer at a time: MMA(A,L), MMA(B,L), MMA(A,L+1) ...
-// so the epilogue of tile A (all 16 epilogue warps, one column quarter each) runs while tile B multiplies and vice
-// versa.  Each tile therefore makes its own pass over the layer's weight chunks; to keep the L2->SM weight stream at
-// one chunk per 256 samples, the two CTAs of a cluster share one ring: each CTA fetches HALF of every chunk and
-// TMA-multicasts it into both CTAs' shared memory.  A ring slot is released when BOTH CTAs' MMAs have retired
-// (tcgen05.commit multicast onto both CTAs' empty barriers).
-// =========================================================================================================
-namespace v6 {
-
-constexpr int OFF_BIAS = OFF_BAR + 128;               // 2 x 1 KB double-buffered bias rows (layer parity)
-constexpr int SMEM6_BYTES = OFF_BIAS + 2048;
-enum { B_W_FULL = 0, B_W_EMPTY = 2, B_ACC_FULL = 4, B_ACT_READY = 6, B_BIAS_FULL = 8 };
-constexpr int EPI_THREADS = 512;
-constexpr int BAR_ID_EPI_ALL = 5;                     // named barrier over all epilogue threads (ids 1-4: row quads)
-
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void tma_bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(mask)
-               : "memory");
-}
-
-// epilogue of one tile-layer for one thread: row `row` of the tile, column quarter `quarter`
-template <int KIND, bool STASH>
-__device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter, uint32_t tmem_row, uint32_t act,
-                                           uint32_t bias_s, const float* __restrict__ aux_g, int quad_bar, const RowSwz sw,
-                                           int64_t s, bool valid) {
-  constexpr int NCB = KIND == EPI_COLOUR ? 1 : 2;  // 32-column blocks per quarter
-  const int cb0 = quarter * NCB;
-  __nv_bfloat16* stp = STASH ? P.st[L] + s * (KIND == EPI_COLOUR ? 128 : 256) : nullptr;
-  float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-  uint32_t buf[2][32];
-  tmem_ld32_issue(tmem_row + cb0 * 32, buf[0]);
-#pragma unroll
-  for (int i = 0; i < NCB; ++i) {
-    const int cb = cb0 + i;
-    uint32_t(&raw)[32] = buf[i & 1];
-    tmem_ld_wait(raw);
-    if (i + 1 < NCB) tmem_ld32_issue(tmem_row + (cb + 1) * 32, buf[(i + 1) & 1]);
-    float4 b4[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) b4[j] = lds128(bias_s + cb * 128 + j * 16);
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) + b4[j].x;
-      v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) + b4[j].y;
-      v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) + b4[j].z;
-      v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) + b4[j].w;
-    }
-    if (KIND == EPI_RELU_SIGMA) {  // sigma head (nerf.py:94, :114); weights from the fp32 side block in L1/L2
-      const float4* __restrict__ ws = reinterpret_cast<const float4*>(aux_g + 7 * AUX_REC_FLOATS + AUX_EXTRA + cb * 32);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 w4 = __ldg(ws + j);
-        sig_acc = fmaf(fmaxf(v[4 * j + 0], 0.f), w4.x, sig_acc);
-        sig_acc = fmaf(fmaxf(v[4 * j + 1], 0.f), w4.y, sig_acc);
-        sig_acc = fmaf(fmaxf(v[4 * j + 2], 0.f), w4.z, sig_acc);
-        sig_acc = fmaf(fmaxf(v[4 * j + 3], 0.f), w4.w, sig_acc);
-      }
-    }
-    if (KIND == EPI_COLOUR) {  // colour head (nerf.py:99, :119) on u = relu(.)
-      const float4* __restrict__ wc = reinterpret_cast<const float4*>(aux_g + 9 * AUX_REC_FLOATS + AUX_EXTRA + cb * 32);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 w0 = __ldg(wc + j), w1 = __ldg(wc + 32 + j), w2 = __ldg(wc + 64 + j);
-        const float u0 = fmaxf(v[4 * j], 0.f), u1 = fmaxf(v[4 * j + 1], 0.f), u2 = fmaxf(v[4 * j + 2], 0.f),
-                    u3 = fmaxf(v[4 * j + 3], 0.f);
-        c0 = fmaf(u0, w0.x, fmaf(u1, w0.y, fmaf(u2, w0.z, fmaf(u3, w0.w, c0))));
-        c1 = fmaf(u0, w1.x, fmaf(u1, w1.y, fmaf(u2, w1.z, fmaf(u3, w1.w, c1))));
-        c2 = fmaf(u0, w2.x, fmaf(u1, w2.y, fmaf(u2, w2.z, fmaf(u3, w2.w, c2))));
-      }
-      if (STASH && valid) {
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd)
-          *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) =
-              make_uint4(pack_bf16_relu(v[8 * qd], v[8 * qd + 1]), pack_bf16_relu(v[8 * qd + 2], v[8 * qd + 3]),
-                         pack_bf16_relu(v[8 * qd + 4], v[8 * qd + 5]), pack_bf16_relu(v[8 * qd + 6], v[8 * qd + 7]));
-      }
-    } else {  // next layer's A operand: K-chunk cb/2 (= this thread's quarter), 16-byte chunks (cb%2)*4 .. +3
-      const uint32_t dst = act + (cb >> 1) * CHUNK_A_BYTES;
-#pragma unroll
-      for (int qd = 0; qd < 4; ++qd) {
-        uint32_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          w[e] = KIND == EPI_LINEAR ? pack_bf16(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1])
-                                    : pack_bf16_relu(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1]);
-        st_shared_v4(sw.addr(dst, (cb & 1) * 4 + qd), w[0], w[1], w[2], w[3]);
-        if (STASH && valid) *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    }
-  }
-  // heads: the 4 column quarters of a row live in warps q, q+4, q+8, q+12 (same TMEM lanes): quarters 1-3 park their
-  // partial sums in accumulator columns they have already drained, quarter 0 adds them up after a 128-thread barrier
-  if (KIND == EPI_RELU_SIGMA || KIND == EPI_COLOUR) {
-    constexpr int QW = KIND == EPI_COLOUR ? 32 : 64;  // columns per quarter
-    if (quarter != 0) tmem_st4(tmem_row + quarter * QW, sig_acc, c0, c1, c2);
-    tc_fence_before();
-    asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
-    tc_fence_after();
-    if (quarter == 0) {
-#pragma unroll
-      for (int q = 1; q < 4; ++q) {
-        float o_s, o0, o1, o2;
-        tmem_ld4(tmem_row + q * QW, o_s, o0, o1, o2);
-        sig_acc += o_s;
-        c0 += o0;
-        c1 += o1;
-        c2 += o2;
-      }
-      if (KIND == EPI_RELU_SIGMA) {
-        const float z = sig_acc + __ldg(aux_g + 7 * AUX_REC_FLOATS + AUX_SIG_B);
-        if (valid) P.sigma[s] = fabsf(z);
-        if (STASH && valid) P.st_zsig[s] = z;
-      } else if (valid) {
-        const float* cbias = aux_g + 9 * AUX_REC_FLOATS + AUX_COL_B;
-        P.rgb[s * 3 + 0] = 1.f / (1.f + __expf(-(c0 + __ldg(cbias))));
-        P.rgb[s * 3 + 1] = 1.f / (1.f + __expf(-(c1 + __ldg(cbias + 1))));
-        P.rgb[s * 3 + 2] = 1.f / (1.f + __expf(-(c2 + __ldg(cbias + 2))));
-      }
-    }
-  }
-}
-
-template <bool STASH>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc6_kernel(const TcParams P) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_rank();
-  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 96);
-  const uint8_t* aux_bytes_g = P.packed + PACKED_W_BYTES;
-  const int iters = (P.num_pairs + (int)gridDim.x - 1) / (int)gridDim.x;  // same trip count in both CTAs of a cluster
-
-  if (threadIdx.x == 0) {
-    if (sbase & 1023) __trap();
-    for (int s = 0; s < N_STAGES; ++s) {
-      mbar_init(bar(B_W_FULL + s), 1);
-      mbar_init(bar(B_W_EMPTY + s), 2);  // one tcgen05.commit from each CTA of the cluster
-    }
-    for (int tl = 0; tl < 2; ++tl) {
-      mbar_init(bar(B_ACC_FULL + tl), 1);
-      mbar_init(bar(B_ACT_READY + tl), EPI_THREADS);
-      mbar_init(bar(B_BIAS_FULL + tl), 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == WARP_MMA) tmem_alloc_512(smem_u32(tmem_slot));
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == WARP_TMA) {
-    // ===================== TMA producer: my half of every chunk, multicast to both CTAs =====================
-    if (lane == 0) {
-      uint32_t q = 0;
-      for (int itp = 0; itp < iters; ++itp) {
-        const uint8_t* src = P.packed;
-        for (int L = 0; L < N_MMA_LAYERS; ++L) {
-          const uint32_t bytes = chunk_bytes(L), hbytes = bytes / 2;
-          for (int tl = 0; tl < 2; ++tl) {
-            for (int kc = 0; kc < layer_chunks(L); ++kc, ++q) {
-              const uint32_t stage = q & 1;
-              mbar_wait(bar(B_W_EMPTY + stage), ((q >> 1) & 1) ^ 1);
-              mbar_expect_tx(bar(B_W_FULL + stage), bytes);
-              tma_bulk_g2s_mc(sbase + OFF_W + stage * W_STAGE_BYTES + crank * hbytes, src + kc * bytes + crank * hbytes,
-                              hbytes, bar(B_W_FULL + stage), (uint16_t)3);
-            }
-          }
-          src += layer_chunks(L) * bytes;
-        }
-      }
-    }
-  } else if (warp == WARP_MMA) {
-    // ===================== MMA issuer: whole layer of tile A, then whole layer of tile B =====================
-    if (lane == 0) {
-      uint32_t q = 0, lit = 0;
-      for (int itp = 0; itp < iters; ++itp) {
-        for (int L = 0; L < N_MMA_LAYERS; ++L, ++lit) {
-          const int nch = layer_chunks(L);
-          const uint32_t idesc = umma_idesc(layer_n(L));
-          for (int tl = 0; tl < 2; ++tl) {
-            mbar_wait(bar(B_ACT_READY + tl), lit & 1);  // operand written + accumulator drained
-            tc_fence_after();
-            if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4)
-              reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + tl * 2] = clock64();
-            const uint32_t d_tmem = tmem_base + tl * 256;
-            for (int kc = 0; kc < nch; ++kc, ++q) {
-              const uint32_t stage = q & 1;
-              mbar_wait(bar(B_W_FULL + stage), (q >> 1) & 1);
-              tc_fence_after();
-              const uint32_t b_addr = sbase + OFF_W + stage * W_STAGE_BYTES;
-              const bool from_enc = (L == 0) || (kc == 4);
-              const uint32_t a_addr = from_enc ? sbase + OFF_ENC + tl * CHUNK_A_BYTES
-                                               : sbase + OFF_ACT + tl * ACT_BYTES + kc * CHUNK_A_BYTES;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma_bf16(d_tmem, umma_desc(a_addr + j * 32), umma_desc(b_addr + j * 32), idesc, (kc | j) != 0);
-              umma_commit_mc(bar(B_W_EMPTY + stage), (uint16_t)3);  // slot free in BOTH CTAs once these MMAs retire
-            }
-            umma_commit(bar(B_ACC_FULL + tl));
-            if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4)
-              reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + tl * 2 + 1] = clock64();
-          }
-        }
-      }
-    }
-  } else {
-    // ===================== 16 encode + epilogue warps, serving tile A and tile B alternately ==================
-    const int quad = warp & 3, quarter = warp >> 2;
-    const int row = quad * 32 + lane;
-    const int quad_bar = 1 + quad;
-    const float* __restrict__ aux_g = reinterpret_cast<const float*>(aux_bytes_g);
-    RowSwz sw;
-    sw.row_off = row * 128;
-    sw.x4 = (row & 7) << 4;
-    const uint32_t tmem_q = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint32_t it = 0;        // per-tile layer counter (acc_full / act_ready parity)
-    uint32_t bias_use[2] = {0, 0};
-    const bool loader = threadIdx.x == 0;
-    if (loader) {  // biases of layers 0 and 1 (1 KB each) into the two buffers
-      for (int b = 0; b < 2; ++b) {
-        mbar_expect_tx(bar(B_BIAS_FULL + b), 1024);
-        tma_bulk_g2s(sbase + OFF_BIAS + b * 1024, aux_bytes_g + b * (AUX_REC_FLOATS * 4), 1024, bar(B_BIAS_FULL + b));
-      }
-    }
-    for (int itp = 0; itp < iters; ++itp) {
-      const int pair = blockIdx.x + itp * (int)gridDim.x;
-      int64_t s_t[2];
-      bool valid_t[2];
-      int64_t ray_t[2];
-      // ---- positional encoding of both tiles' samples: this thread = one row, feature pairs 8*quarter .. +7 ----
-#pragma unroll
-      for (int tl = 0; tl < 2; ++tl) {
-        const int64_t s = ((int64_t)pair * 2 + tl) * TILE_M + row;
-        const bool valid = pair < P.num_pairs && s < P.total;
-        const int64_t sc = valid ? s : P.total - 1;
-        const int64_t ray = sc / P.p;
-        s_t[tl] = s;
-        valid_t[tl] = valid;
-        ray_t[tl] = ray;
-        const float4* rp = reinterpret_cast<const float4*>(P.rays + ray * 16);
-        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
-        const float tt = __ldg(P.t + sc);
-        const float pc0 = __fmul_rn(r0.x, tt), pc1 = __fmul_rn(r0.y, tt), pc2 = __fmul_rn(r0.z, tt);
-        float pos[3];
-        pos[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.w, pc0), __fmul_rn(r1.x, pc1)), __fmul_rn(r1.y, pc2)), r3.x);
-        pos[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.z, pc0), __fmul_rn(r1.w, pc1)), __fmul_rn(r2.x, pc2)), r3.y);
-        pos[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.y, pc0), __fmul_rn(r2.z, pc1)), __fmul_rn(r2.w, pc2)), r3.z);
-        uint32_t f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int pi = quarter * 8 + i;  // feature pair index = c*10 + l
-          if (pi < 30) {
-            const int c = pi / 10, l = pi % 10;
-            const float x = c == 0 ? pos[0] : (c == 1 ? pos[1] : pos[2]);
-            float sn, cs;
-            fast_sincos(__fmul_rn(__uint_as_float(c_tc_freq_point[l]), x), sn, cs);
-            f[i] = pack_bf16(sn, cs);
-          } else {
-            f[i] = 0u;  // K padded 60 -> 64
-          }
-        }
-        const uint32_t enc = sbase + OFF_ENC + tl * CHUNK_A_BYTES;
-        st_shared_v4(sw.addr(enc, quarter * 2), f[0], f[1], f[2], f[3]);
-        st_shared_v4(sw.addr(enc, quarter * 2 + 1), f[4], f[5], f[6], f[7]);
-        if (STASH && valid) {
-          uint4* d = reinterpret_cast<uint4*>(P.st_enc + s * 64 + quarter * 16);
-          d[0] = make_uint4(f[0], f[1], f[2], f[3]);
-          d[1] = make_uint4(f[4], f[5], f[6], f[7]);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(bar(B_ACT_READY + tl));
-      }
-
-      for (int L = 0; L < N_MMA_LAYERS; ++L, ++it) {
-        const int bb = L & 1;
-        const uint32_t bias_s = sbase + OFF_BIAS + bb * 1024;
-#pragma unroll
-        for (int tl = 0; tl < 2; ++tl) {
-          const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
-          const uint32_t enc = sbase + OFF_ENC + tl * CHUNK_A_BYTES;
-          const uint32_t tmem_row = tmem_q + tl * 256;
-          mbar_wait(bar(B_ACC_FULL + tl), it & 1);
-          tc_fence_after();
-          if (tl == 0) mbar_wait(bar(B_BIAS_FULL + bb), bias_use[bb] & 1);
-          if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
-            reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 4 + tl * 2] = clock64();
-          if (L == 7)
-            epilogue_q<EPI_RELU_SIGMA, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
-          else if (L == 8)
-            epilogue_q<EPI_LINEAR, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
-          else if (L == 9)
-            epilogue_q<EPI_COLOUR, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
-          else
-            epilogue_q<EPI_RELU, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
-          if (L == 4) {
-            // the xyz features of this tile are dead (all its MMAs retired): store the view features in their place
-            if (quarter == 0) {
-              const float4* de = reinterpret_cast<const float4*>(P.dir_enc + ray_t[tl] * 24);
-              uint32_t f[12];
-#pragma unroll
-              for (int j = 0; j < 6; ++j) {
-                const float4 d4 = __ldg(de + j);
-                f[2 * j] = pack_bf16(d4.x, d4.y);
-                f[2 * j + 1] = pack_bf16(d4.z, d4.w);
-              }
-#pragma unroll
-              for (int j = 0; j < 3; ++j) st_shared_v4(sw.addr(enc, j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-              st_shared_v4(sw.addr(enc, 3), 0u, 0u, 0u, 0u);
-              if (STASH && valid_t[tl]) {
-                uint4* d = reinterpret_cast<uint4*>(P.st_denc + s_t[tl] * 32);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) d[j] = make_uint4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                d[3] = make_uint4(0u, 0u, 0u, 0u);
-              }
-            } else if (quarter == 1) {
-#pragma unroll
-              for (int j = 4; j < 8; ++j) st_shared_v4(sw.addr(enc, j), 0u, 0u, 0u, 0u);
-            }
-          }
-          if (L != 9) {
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(bar(B_ACT_READY + tl));
-          }
-          if (P.dbg_layer >= 100 && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
-            reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 5 + tl * 2] = clock64();
-        }
-        // both tiles are done with this layer's bias row: refill the buffer with layer L+2's (next pair's for L = 8, 9)
-        ++bias_use[bb];
-        asm volatile("bar.sync %0, %1;" ::"r"(BAR_ID_EPI_ALL), "r"(EPI_THREADS) : "memory");
-        if (loader) {
-          const int Ln = (L + 2) % N_MMA_LAYERS;
-          const bool more = (L + 2 < N_MMA_LAYERS) || (itp + 1 < iters);
-          if (more) {
-            fence_proxy_async();
-            mbar_expect_tx(bar(B_BIAS_FULL + bb), 1024);
-            tma_bulk_g2s(sbase + OFF_BIAS + bb * 1024, aux_bytes_g + Ln * (AUX_REC_FLOATS * 4), 1024, bar(B_BIAS_FULL + bb));
-          }
-        }
-      }
-    }
-  }
-
-  __syncwarp();
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
-  if (warp == WARP_MMA) {
-    tc_fence_after();
-    tmem_dealloc_512(tmem_base);
-  }
-}
-
-}  // namespace v6
 
 // =========================================================================================================
 // v7: tile-STAGGERED schedule with CTA-PAIR MMAs (tcgen05 cta_group::2).
@@ -1057,9 +494,13 @@ __device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint
       : "memory");
 }
 // M = 256 (both CTAs' 128 rows), D = f32, A = B = bf16, K-major
-__host__ __device__ constexpr uint32_t umma2_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
+template <bool F16>
+__host__ __device__ constexpr uint32_t umma2_idesc(int n) { return idesc_f16kind(256, n, !F16); }
+// 16-bit operand packing of the schedule's precision: bf16 (NT_PREC_BF16) or saturating fp16 (NT_PREC_FP16)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) { return F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16_relu(float lo, float hi) { return F16 ? pack_f16_relu(lo, hi) : pack_bf16_relu(lo, hi); }
 // shared-memory matrix descriptor (K-major, SWIZZLE_128B, SBO 1024 B) split into its constant high word and the
 // address word: advancing K by 16 bf16 (32 B) is +2 on the low word
 constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
@@ -1084,45 +525,6 @@ __device__ __forceinline__ void remote_arrive(uint32_t local_bar, uint32_t targe
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_bar), "r"(target_cta));
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
-// non-blocking poll.  The leader's barriers are completed by REMOTE arrives (the peer's relays): a thread suspended inside
-// mbarrier.try_wait is not woken by those and sleeps out the hardware time limit (~700 clk measured), so the MMA thread
-// polls with test_wait instead.
-__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done;
-}
-__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
-  long long t0 = 0;
-  int spins = 0;
-  while (!mbar_try(bar, parity)) {
-    if (++spins == 4096) t0 = clock64();
-    if (spins > 4096 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  long long t0 = 0;
-  int spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins == 1024) t0 = clock64();
-    if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
-  }
-}
 __device__ __forceinline__ void tmem2_alloc_512(uint32_t smem_slot) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_slot) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -1132,13 +534,12 @@ __device__ __forceinline__ void tmem2_dealloc_512(uint32_t taddr) {
 }
 
 // epilogue of one tile-layer for one thread: row `row` of the tile, column quarter `quarter`
-template <int KIND, bool STASH>
+template <int KIND, bool F16>
 __device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter, uint32_t tmem_row, uint32_t act,
                                            uint32_t bias_s, const float* __restrict__ aux_g, int quad_bar, const RowSwz sw,
                                            int64_t s, bool valid) {
   constexpr int NCB = KIND == EPI_COLOUR ? 1 : 2;  // 32-column blocks per quarter
   const int cb0 = quarter * NCB;
-  __nv_bfloat16* stp = STASH ? P.st[L] + s * (KIND == EPI_COLOUR ? 128 : 256) : nullptr;
   float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
   uint32_t buf[2][32];
   tmem_ld32_issue(tmem_row + cb0 * 32, buf[0]);
@@ -1179,13 +580,6 @@ __device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter
         c1 = fmaf(u0, w1.x, fmaf(u1, w1.y, fmaf(u2, w1.z, fmaf(u3, w1.w, c1))));
         c2 = fmaf(u0, w2.x, fmaf(u1, w2.y, fmaf(u2, w2.z, fmaf(u3, w2.w, c2))));
       }
-      if (STASH && valid) {
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd)
-          *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) =
-              make_uint4(pack_bf16_relu(v[8 * qd], v[8 * qd + 1]), pack_bf16_relu(v[8 * qd + 2], v[8 * qd + 3]),
-                         pack_bf16_relu(v[8 * qd + 4], v[8 * qd + 5]), pack_bf16_relu(v[8 * qd + 6], v[8 * qd + 7]));
-      }
     } else {  // next layer's A operand: K-chunk cb/2 (= this thread's quarter), 16-byte chunks (cb%2)*4 .. +3
       const uint32_t dst = act + (cb >> 1) * CHUNK_A_BYTES;
 #pragma unroll
@@ -1193,10 +587,9 @@ __device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          w[e] = KIND == EPI_LINEAR ? pack_bf16(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1])
-                                    : pack_bf16_relu(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1]);
+          w[e] = KIND == EPI_LINEAR ? pack16<F16>(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1])
+                                    : pack16_relu<F16>(v[8 * qd + 2 * e], v[8 * qd + 2 * e + 1]);
         st_shared_v4(sw.addr(dst, (cb & 1) * 4 + qd), w[0], w[1], w[2], w[3]);
-        if (STASH && valid) *reinterpret_cast<uint4*>(stp + cb * 32 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }
@@ -1221,7 +614,6 @@ __device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter
       if (KIND == EPI_RELU_SIGMA) {
         const float z = sig_acc + __ldg(aux_g + 7 * AUX_REC_FLOATS + AUX_SIG_B);
         if (valid) P.sigma[s] = fabsf(z);
-        if (STASH && valid) P.st_zsig[s] = z;
       } else if (valid) {
         const float* cbias = aux_g + 9 * AUX_REC_FLOATS + AUX_COL_B;
         P.rgb[s * 3 + 0] = 1.f / (1.f + __expf(-(c0 + __ldg(cbias))));
@@ -1232,7 +624,7 @@ __device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter
   }
 }
 
-template <bool STASH, bool TL>
+template <bool F16, bool TL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc7_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -1329,7 +721,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
         for (int L = 0; L < N_MMA_LAYERS; ++L, ++lit) {
           const int nch = layer_chunks(L);
           const bool five = nch == 5;
-          const uint32_t idesc = umma2_idesc(layer_n(L));
+          const uint32_t idesc = umma2_idesc<F16>(layer_n(L));
 #pragma unroll
           for (int tl = 0; tl < 2; ++tl) {
             // loads used by this pass: tile A = loads 0..nch-1 (all first uses), tile B = the resident chunks again and,
@@ -1447,7 +839,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
             const float x = c == 0 ? pos[0] : (c == 1 ? pos[1] : pos[2]);
             float sn, cs;
             fast_sincos(__fmul_rn(__uint_as_float(c_tc_freq_point[l]), x), sn, cs);
-            f[i] = pack_bf16(sn, cs);
+            f[i] = pack16<F16>(sn, cs);
           } else {
             f[i] = 0u;  // K padded 60 -> 64
           }
@@ -1455,11 +847,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
         const uint32_t enc = sbase + OFF_ENC + tl * CHUNK_A_BYTES;
         st_shared_v4(sw.addr(enc, quarter * 2), f[0], f[1], f[2], f[3]);
         st_shared_v4(sw.addr(enc, quarter * 2 + 1), f[4], f[5], f[6], f[7]);
-        if (STASH && valid) {
-          uint4* d = reinterpret_cast<uint4*>(P.st_enc + s * 64 + quarter * 16);
-          d[0] = make_uint4(f[0], f[1], f[2], f[3]);
-          d[1] = make_uint4(f[4], f[5], f[6], f[7]);
-        }
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar(B_ACT_READY + tl));
@@ -1479,13 +866,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
           if (TL && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
             reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 4 + tl * 2] = clock64();
           if (L == 7)
-            epilogue_q<EPI_RELU_SIGMA, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+            epilogue_q<EPI_RELU_SIGMA, F16>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
           else if (L == 8)
-            epilogue_q<EPI_LINEAR, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+            epilogue_q<EPI_LINEAR, F16>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
           else if (L == 9)
-            epilogue_q<EPI_COLOUR, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+            epilogue_q<EPI_COLOUR, F16>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
           else
-            epilogue_q<EPI_RELU, STASH>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+            epilogue_q<EPI_RELU, F16>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
           if (L == 4) {
             // the xyz features of this tile are dead (all its MMAs retired): store the view features in their place
             if (quarter == 0) {
@@ -1494,18 +881,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
 #pragma unroll
               for (int j = 0; j < 6; ++j) {
                 const float4 d4 = __ldg(de + j);
-                f[2 * j] = pack_bf16(d4.x, d4.y);
-                f[2 * j + 1] = pack_bf16(d4.z, d4.w);
+                f[2 * j] = pack16<F16>(d4.x, d4.y);
+                f[2 * j + 1] = pack16<F16>(d4.z, d4.w);
               }
 #pragma unroll
               for (int j = 0; j < 3; ++j) st_shared_v4(sw.addr(enc, j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
               st_shared_v4(sw.addr(enc, 3), 0u, 0u, 0u, 0u);
-              if (STASH && valid_t[tl]) {
-                uint4* d = reinterpret_cast<uint4*>(P.st_denc + s_t[tl] * 32);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) d[j] = make_uint4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                d[3] = make_uint4(0u, 0u, 0u, 0u);
-              }
             } else if (quarter == 1) {
 #pragma unroll
               for (int j = 4; j < 8; ++j) st_shared_v4(sw.addr(enc, j), 0u, 0u, 0u, 0u);
@@ -1559,7 +940,10 @@ struct PackParams {
   int sig_w, sig_b, col_w, col_b;
 };
 
-__global__ void pack_weights_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed, PackParams pp) {
+// mode 0: bf16, 1: fp16 (same layout), 2: split fp16 for NT_PREC_TC32 — every chunk is followed by the chunk of its scaled
+// residuals, lo = fp16((w - hi) * 2^12), and the fp32 side block sits behind the doubled image
+__global__ void pack_weights_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed, PackParams pp, int mode) {
+  const int w_bytes = mode == 2 ? 2 * PACKED_W_BYTES : PACKED_W_BYTES;
   // one thread per 16-byte chunk (8 bf16) of the packed image, then one per float of the fp32 side block
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= PACKED_W_BYTES / 16) {
@@ -1577,14 +961,15 @@ __global__ void pack_weights_kernel(const float* __restrict__ params, uint8_t* _
       v = params[pp.sig_b];
     else if (L == 9 && i >= AUX_EXTRA)
       v = params[pp.col_w + (i - AUX_EXTRA)];
-    reinterpret_cast<float*>(packed + PACKED_W_BYTES)[a] = v;
+    reinterpret_cast<float*>(packed + w_bytes)[a] = v;
     return;
   }
-  int byte = gid * 16, L = 0, kc = 0;
+  int byte = gid * 16, L = 0, kc = 0, base = 0;
   for (L = 0; L < N_MMA_LAYERS; ++L) {
     const int lb = layer_chunks(L) * chunk_bytes(L);
     if (byte < lb) break;
     byte -= lb;
+    base += lb;
   }
   kc = byte / chunk_bytes(L);
   byte -= kc * chunk_bytes(L);
@@ -1592,7 +977,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ params, uint8_t* _
   const int jphys = (byte % 128) / 16;
   const int j = jphys ^ (n & 7);  // logical 16-byte chunk stored at this swizzled position
   const PackLayer pl = pp.layer[L];
-  uint32_t out[4];
+  uint32_t out[4], out_lo[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     float v[2];
@@ -1610,10 +995,19 @@ __global__ void pack_weights_kernel(const float* __restrict__ params, uint8_t* _
         col = kc * 64 + k;
       v[h] = col >= 0 ? params[pl.w_off + (int64_t)n * pl.ld + col] : 0.f;
     }
-    __nv_bfloat162 b = __floats2bfloat162_rn(v[0], v[1]);
-    out[e] = *reinterpret_cast<uint32_t*>(&b);
+    out[e] = mode ? pack_f16(v[0], v[1]) : pack_bf16(v[0], v[1]);
+    if (mode == 2) {
+      const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&out[e]));
+      out_lo[e] = pack_f16((v[0] - h.x) * 4096.f, (v[1] - h.y) * 4096.f);
+    }
   }
-  *reinterpret_cast<uint4*>(packed + (size_t)gid * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+  if (mode == 2) {
+    uint8_t* dst = packed + 2 * (size_t)base + (size_t)kc * 2 * chunk_bytes(L) + byte;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<uint4*>(dst + chunk_bytes(L)) = make_uint4(out_lo[0], out_lo[1], out_lo[2], out_lo[3]);
+  } else {
+    *reinterpret_cast<uint4*>(packed + (size_t)gid * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
 }
 
 const int kMmaLayerIndex[N_MMA_LAYERS] = {L_P0, L_P1, L_P2, L_P3, L_P4, L_P5, L_P6, L_P7, L_INFO, L_DIR};
@@ -1622,7 +1016,7 @@ const int kMmaLayerIndex[N_MMA_LAYERS] = {L_P0, L_P1, L_P2, L_P3, L_P4, L_P5, L_
 
 size_t nt_mlp_tc_packed_bytes() { return PACKED_BYTES; }
 
-int nt_mlp_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t st) {
+int nt_mlp_tc_pack(nt_ctx* ctx, const float* params, void* packed, int mode, cudaStream_t st) {
   const LayerTable T = nt_layers();
   PackParams pp;
   for (int i = 0; i < N_MMA_LAYERS; ++i) {
@@ -1637,20 +1031,23 @@ int nt_mlp_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t 
   pp.col_w = (int)T.w[L_COLOR];
   pp.col_b = (int)T.b[L_COLOR];
   const int threads = PACKED_W_BYTES / 16 + AUX_FLOATS;
-  pack_weights_kernel<<<(threads + 255) / 256, 256, 0, st>>>(params, (uint8_t*)packed, pp);
+  pack_weights_kernel<<<(threads + 255) / 256, 256, 0, st>>>(params, (uint8_t*)packed, pp, mode);
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;
 }
 
 static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                          const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int dbg_layer,
-                         const TcStash* stash, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+                         const TcStash* stash, int fp16, cudaStream_t st) {
+  if (fp16 && (stash || (dbg && dbg_layer < 100))) {
+    nt_set_error("NT_PREC_FP16 operands are a rendering mode: training / the per-layer dump run on the bf16 kernels");
+    return NT_ERR_UNSUPPORTED;
+  }
+  if (!(ctx->attr_done & NT_ATTR_MLP_TC5)) {
     NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    ctx->attr_done |= NT_ATTR_MLP_TC5;
   }
   TcParams P;
   memset(&P, 0, sizeof(P));
@@ -1697,34 +1094,26 @@ static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const fl
     const char* e = getenv("NT_MLP_TC_VERSION");
     ver = e ? atoi(e) : 7;
   }
-  const bool use_v6 = ver == 6, use_v7 = ver == 7;
-  if (use_v7 && (!dbg || dbg_layer >= 100) && !stash) {
-    static bool set7 = false;
-    if (!set7) {
+  const bool use_v7 = ver == 7;
+  if ((use_v7 || fp16) && (!dbg || dbg_layer >= 100) && !stash) {
+    if (!(ctx->attr_done & NT_ATTR_MLP_TC7)) {
       NT_CUDA(cudaFuncSetAttribute(v7::mlp_tc7_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::SMEM7_BYTES));
       NT_CUDA(cudaFuncSetAttribute(v7::mlp_tc7_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::SMEM7_BYTES));
-      set7 = true;
+      NT_CUDA(cudaFuncSetAttribute(v7::mlp_tc7_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::SMEM7_BYTES));
+      NT_CUDA(cudaFuncSetAttribute(v7::mlp_tc7_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v7::SMEM7_BYTES));
+      ctx->attr_done |= NT_ATTR_MLP_TC7;
     }
     int g7 = ctx->sm_count & ~1;                       // whole 2-CTA clusters
     const int need = ((P.num_pairs + 1) / 2) * 2;
     if (g7 > need) g7 = need;
-    if (dbg)
+    if (dbg && fp16)
+      v7::mlp_tc7_kernel<true, true><<<g7, N_THREADS, v7::SMEM7_BYTES, st>>>(P);
+    else if (dbg)
       v7::mlp_tc7_kernel<false, true><<<g7, N_THREADS, v7::SMEM7_BYTES, st>>>(P);
+    else if (fp16)
+      v7::mlp_tc7_kernel<true, false><<<g7, N_THREADS, v7::SMEM7_BYTES, st>>>(P);
     else
       v7::mlp_tc7_kernel<false, false><<<g7, N_THREADS, v7::SMEM7_BYTES, st>>>(P);
-    NT_LAUNCH_CHECK(ctx);
-    return NT_OK;
-  }
-  if (use_v6 && (!dbg || dbg_layer >= 100) && !stash) {
-    static bool set6 = false;
-    if (!set6) {
-      NT_CUDA(cudaFuncSetAttribute(v6::mlp_tc6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v6::SMEM6_BYTES));
-      set6 = true;
-    }
-    int g6 = ctx->sm_count & ~1;                       // whole 2-CTA clusters
-    const int need = ((P.num_pairs + 1) / 2) * 2;
-    if (g6 > need) g6 = need;
-    v6::mlp_tc6_kernel<false><<<g6, N_THREADS, v6::SMEM6_BYTES, st>>>(P);
     NT_LAUNCH_CHECK(ctx);
     return NT_OK;
   }
@@ -1741,14 +1130,14 @@ static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const fl
 int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                           const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int dbg_layer,
                           cudaStream_t st) {
-  return mlp_tc_launch(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, dbg, dbg_layer, nullptr, st);
+  return mlp_tc_launch(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, dbg, dbg_layer, nullptr, 0, st);
 }
 int nt_mlp_tc_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
-                      const float* params, const void* packed, float* rgb, float* sigma, cudaStream_t st) {
-  return mlp_tc_launch(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, nullptr, -1, nullptr, st);
+                      const float* params, const void* packed, float* rgb, float* sigma, int fp16, cudaStream_t st) {
+  return mlp_tc_launch(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, nullptr, -1, nullptr, fp16, st);
 }
 int nt_mlp_tc_forward_stash(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                             const float* params, const void* packed, float* rgb, float* sigma, const TcStash* stash,
                             cudaStream_t st) {
-  return mlp_tc_launch(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, nullptr, -1, stash, st);
+  return mlp_tc_launch(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, nullptr, -1, stash, 0, st);
 }

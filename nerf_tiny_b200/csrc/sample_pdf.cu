@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(PDF_WARPS * 32)
 
 extern "C" int nt_sample_pdf(nt_ctx* ctx, int64_t n, const float* t_coarse, const float* w, const float* delta0,
                              float* t_fine, int32_t* idx, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && t_coarse && w && t_fine, "null pointer");
   NT_REQUIRE(ctx->n_coarse == NC && ctx->n_fine == NF, "sample_pdf is built for Nc=64, Nf=128");
   if (n <= 0) return NT_OK;
@@ -164,6 +165,7 @@ extern "C" int nt_sample_pdf(nt_ctx* ctx, int64_t n, const float* t_coarse, cons
 
 extern "C" int nt_sample_pdf_backward(nt_ctx* ctx, int64_t n, const float* t_coarse, const float* w,
                                       const float* delta0, const float* g_t_fine, float* g_w, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx && t_coarse && w && g_t_fine && g_w, "null pointer");
   NT_REQUIRE(ctx->n_coarse == NC && ctx->n_fine == NF, "sample_pdf is built for Nc=64, Nf=128");
   if (n <= 0) return NT_OK;
@@ -174,6 +176,7 @@ extern "C" int nt_sample_pdf_backward(nt_ctx* ctx, int64_t n, const float* t_coa
 }
 
 extern "C" int nt_check_status(nt_ctx* ctx, void* stream) {
+  NT_ENTER(ctx);
   NT_REQUIRE(ctx, "null ctx");
   int h = 0;
   NT_CUDA(cudaMemcpyAsync(&h, ctx->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));

@@ -61,6 +61,53 @@ def global_quantities(near_local: np.ndarray, far_local: np.ndarray, group=None,
     return zero, delta0_of(first[0].item(), first[1].item(), zero, n_coarse)
 
 
+class ShardGlobals:
+    """The same two quantities for the CUDA path, reduced ON THE DEVICE (no host round trip): each rank's
+    `nt_shard_globals_local` writes {flag, delta0 candidate if flag == 0, candidate if flag == 1, 0} (candidates = -inf
+    unless it owns global ray 0), ONE element-wise MAX all-reduce of those 16 bytes makes them global, and
+    `nt_shard_globals_resolve` leaves g[0] = delta0, g[1] = any_step_zero where the render kernels read them.
+
+    `reduce_max(t)`: in-place MAX reduction of the 4-float device tensor over the shards; defaults to
+    torch.distributed.all_reduce(MAX) on `group` (NCCL on GPUs).  Tests that emulate several shards on one GPU pass their
+    own."""
+
+    def __init__(self, rank: int, world: int, group=None, reduce_max=None):
+        self.rank, self.world, self.group, self.reduce_max = int(rank), int(world), group, reduce_max
+        if reduce_max is None and self.world > 1:
+            if not dist.is_initialized():
+                raise RuntimeError("shard=(rank, world) with world > 1 needs an initialised torch.distributed group")
+            if dist.get_world_size(group) != self.world or dist.get_rank(group) != self.rank:
+                raise RuntimeError("shard=(%d, %d) does not match the process group (rank %d of %d)" %
+                                   (self.rank, self.world, dist.get_rank(group), dist.get_world_size(group)))
+
+    def local(self, model, near: torch.Tensor, far: torch.Tensor) -> torch.Tensor:
+        import ctypes as C
+        from . import _lib
+        dev = model._ensure_ctx()
+        g = torch.empty(4, dtype=torch.float32, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        n = int(near.shape[0])
+        _lib.check(model._lib.nt_shard_globals_local(model._ctx, n, C.c_void_p(near.data_ptr() if n else 0),
+                                                     C.c_void_p(far.data_ptr() if n else 0), 1 if self.rank == 0 else 0,
+                                                     C.c_void_p(g.data_ptr()), st))
+        return g
+
+    def resolve(self, model, g: torch.Tensor) -> torch.Tensor:
+        import ctypes as C
+        from . import _lib
+        st = C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+        _lib.check(model._lib.nt_shard_globals_resolve(model._ctx, C.c_void_p(g.data_ptr()), st))
+        return g
+
+    def compute(self, model, near: torch.Tensor, far: torch.Tensor) -> torch.Tensor:
+        g = self.local(model, near, far)
+        if self.reduce_max is not None:
+            self.reduce_max(g)
+        elif self.world > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.MAX, group=self.group)
+        return self.resolve(model, g)
+
+
 def allreduce_sum_(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
     """One collective over the flat 593 924-float gradient (2 375 696 B); NCCL over NVLink on GPUs."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:

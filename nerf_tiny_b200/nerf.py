@@ -15,6 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import pickle as _pickle
 import random
 import time
 
@@ -27,7 +28,13 @@ from . import _lib
 writer = None
 device = None
 
-PRECISION = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+# MLP arithmetic (include/nerftiny.h NT_PREC_*).  "fp16" / "bf16": single-pass 16-bit tcgen05 kernels (fp16 operands round 8x
+# finer than bf16 at the same speed; the network's activations are bounded, so fp16 is the default for rendering);
+# "tc32": 3-pass split-fp16 tcgen05 kernel meeting the fp32 tolerance on the tensor cores; "fp32": CUDA-core FFMA.
+# Training runs on the bf16 tensor-core path for "bf16" / "fp16" and on the fp32 path for "fp32" / "tc32".
+PRECISION = {"fp32": _lib.PREC_FP32, "tc32": _lib.PREC_TC32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
+TRAIN_PRECISION = {"fp32": _lib.PREC_FP32, "tc32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_BF16}
+DEFAULT_PRECISION = "fp16"
 
 
 def seed_everything(seed):
@@ -54,8 +61,9 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(dev=None):
+    """The caller's current stream ON `dev` (the model's device), whatever device is current."""
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def _dev_f32(t, dev):
@@ -79,10 +87,11 @@ def _module_ctx(dev):
 
 
 class Activation(nn.Module):
-    """nerf.py:69-74 (sigma = |x|).  Fused into the MLP kernels; kept for state_dict/module-tree parity."""
+    """nerf.py:69-74 (sigma = |x|).  Inside Network / NeRFModel the abs is fused into the CUDA MLP kernels; called on its
+    own it is the reference's one-liner (nerf.py:73-74)."""
 
     def forward(self, x):
-        raise _lib.NerfTinyError("Activation is fused into the CUDA MLP kernels; call Network/NeRFModel instead")
+        return torch.abs(x)
 
 
 class Network(nn.Module):
@@ -107,6 +116,7 @@ class Network(nn.Module):
         self.color_layer = nn.Sequential(nn.Linear(width // 2, 3), nn.Sigmoid())
         self._flat = None
         self._flat_grad = None
+        self._grad_external = None
         self._flatten()
 
     # -- flat parameter storage ------------------------------------------------------------------
@@ -114,7 +124,12 @@ class Network(nn.Module):
         params = list(self.parameters())
         dev = dev if dev is not None else params[0].device
         flat = torch.empty(_lib.N_PARAMS, dtype=torch.float32, device=dev)
-        grad = torch.zeros(_lib.N_PARAMS, dtype=torch.float32, device=dev)
+        ext = getattr(self, "_grad_external", None)
+        if ext is not None and ext.device == flat.device:
+            grad = ext.zero_()          # keep an installed gradient buffer (symmetric / peer-mapped memory) across re-flattens
+        else:
+            self._grad_external = None
+            grad = torch.zeros(_lib.N_PARAMS, dtype=torch.float32, device=dev)
         off = 0
         for p in params:
             n = p.numel()
@@ -146,6 +161,7 @@ class Network(nn.Module):
         assert buf.numel() == _lib.N_PARAMS and buf.dtype == torch.float32
         buf.copy_(self._flat_grad)
         self._flat_grad = buf
+        self._grad_external = buf
         off = 0
         for p in self.parameters():
             n = p.numel()
@@ -181,7 +197,7 @@ class Network(nn.Module):
         need = max(256, lib.nt_mlp_workspace_bytes(h, _lib.PREC_FP32, n * p, 1, 0))
         ws = torch.empty(need, dtype=torch.uint8, device=flat.device)
         _lib.check(lib.nt_network_forward(h, n * p, _ptr(enc_p), _ptr(enc_d), _ptr(flat.detach()), _ptr(color), _ptr(sigma),
-                                          _ptr(ws), ws.numel(), _stream()))
+                                          _ptr(ws), ws.numel(), _stream(flat.device)))
         return color, sigma
 
 
@@ -206,7 +222,7 @@ class Encoder(nn.Module):
         pt, dr = _dev_f32(point, dev), _dev_f32(dir, dev)
         g_p = torch.empty(n, p, 3, 2 * self.L_point, dtype=torch.float32, device=dev)
         g_d = torch.empty(n, p, 3, 2 * self.L_dir, dtype=torch.float32, device=dev)
-        _lib.check(lib.nt_encode(h, n * p, _ptr(pt), _ptr(dr), _ptr(g_p), _ptr(g_d), _stream()))
+        _lib.check(lib.nt_encode(h, n * p, _ptr(pt), _ptr(dr), _ptr(g_p), _ptr(g_d), _stream(dev)))
         return g_p, g_d
 
 
@@ -214,9 +230,10 @@ class _RenderFn(torch.autograd.Function):
     """render_rays forward/backward as one autograd node (nerf.py:286-323 + nerf.py:473)."""
 
     @staticmethod
-    def forward(ctx, model, flat, row, col, pose17, kinv, near, far):
-        cc, cf, ws = model._render_raw(flat, row, col, pose17, kinv, near, far, train=True)
-        ctx.model, ctx.ws, ctx.near, ctx.far, ctx.flat = model, ws, near, far, flat
+    def forward(ctx, model, flat, row, col, pose17, kinv, near, far, any_step_zero, delta0):
+        cc, cf, ws = model._render_raw(flat, row, col, pose17, kinv, near, far, train=True, any_step_zero=any_step_zero,
+                                       delta0=delta0)
+        ctx.model, ctx.ws, ctx.near, ctx.far, ctx.flat, ctx.delta0 = model, ws, near, far, flat, delta0
         return cc, cf
 
     @staticmethod
@@ -226,27 +243,46 @@ class _RenderFn(torch.autograd.Function):
         n = ctx.near.shape[0]
         g_cc = g_cc.contiguous().float()
         g_cf = g_cf.contiguous().float()
-        _lib.check(m._lib.nt_render_backward(m._ctx, m._prec_train, n, _ptr(ctx.near), _ptr(ctx.far), _ptr(ctx.flat),
-                                             _ptr(m._packed), None, _ptr(g_cc), _ptr(g_cf), _ptr(grads), _ptr(ctx.ws),
-                                             ctx.ws.numel(), _stream()))
+        prec = m._prec_train
+        _lib.check(m._lib.nt_render_backward(m._ctx, prec, n, _ptr(ctx.near), _ptr(ctx.far), _ptr(ctx.flat),
+                                             _ptr(m._packed.get(prec)), _ptr(ctx.delta0), _ptr(g_cc), _ptr(g_cf), _ptr(grads),
+                                             _ptr(ctx.ws), ctx.ws.numel(), _stream(ctx.flat.device)))
         ctx.ws = None
-        return None, grads, None, None, None, None, None, None
+        return None, grads, None, None, None, None, None, None, None, None
 
 
 class NeRFModel(nn.Module):
-    """nerf.py:169-348.  `precision` ("bf16" tcgen05 path / "fp32" accuracy path) is the one extra knob."""
+    """nerf.py:169-348.  `precision` is the one extra knob (see PRECISION above; default "fp16", or $NERF_TINY_PRECISION).
+
+    Ray sharding: `forward`, `render_rays`, `train_step` and `GraphedTrainStep` take `shard=`
+      None                      this call holds the whole batch (the reference's situation);
+      (rank, world)             this call holds rank's contiguous slice of a batch sharded over `world` processes of the
+                                default torch.distributed group: the two batch-global quantities (numpy's any_step_zero
+                                branch, nerf.py:288, and delta0 of global ray 0, nerf.py:234) are reduced on the device
+                                (one 16-byte MAX all-reduce, no host sync) so that sharded == unsharded bit for bit;
+      a dist.ShardGlobals       the same with an explicit group / reduction;
+      {"any_step_zero": 0|1, "delta0": tensor[1]}   explicit values.
+    """
 
     def __init__(self, num_coarse=64, num_fine=128, batch_ray=8, precision=None):
         super().__init__()
         self.encoder = Encoder(batch_size=batch_ray)
         self.network = Network(batch_size=batch_ray)
         self.num_coarse, self.num_fine, self.batch_ray = num_coarse, num_fine, batch_ray
-        self.precision = precision or os.environ.get("NERF_TINY_PRECISION", "bf16")
+        self.precision = precision or os.environ.get("NERF_TINY_PRECISION", DEFAULT_PRECISION)
+        if self.precision not in PRECISION:
+            raise _lib.NerfTinyError("precision must be one of %s" % sorted(PRECISION))
+        self.check_range = True          # raise (the reference: exit(0)) right after forward
+        self._init_runtime()
+
+    def _init_runtime(self):
         self._lib = _lib.load()          # raises if the extension is missing: no fallback
         self._ctx = None
-        self._packed = None
+        self._ctx_dev = None
+        self._packed = {}                # precision code -> packed weight image
         self._ws_cache = {}
-        self.check_range = True          # raise (the reference: exit(0)) right after forward
+        self._shards = {}
+        self._last = 1e-4
 
     # -- context -----------------------------------------------------------------------------------
     def _ensure_ctx(self):
@@ -254,13 +290,15 @@ class NeRFModel(nn.Module):
         if dev.type != "cuda":
             raise _lib.NerfTinyError("NeRFModel lives on %s: move it to a CUDA device (no CPU path exists)" % dev)
         if self._ctx is None or self._ctx_dev != dev:
+            if self._ctx is not None:
+                self._lib.nt_destroy(self._ctx)
             h = C.c_void_p()
             idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            dev = torch.device("cuda", idx)
             _lib.check(self._lib.nt_create(C.byref(h), idx, self.num_coarse, self.num_fine))
             self._ctx, self._ctx_dev = h, dev
-            self._packed = torch.empty(max(256, self._lib.nt_packed_weight_bytes(h, _lib.PREC_BF16)), dtype=torch.uint8,
-                                       device=dev)
-        return dev
+            self._packed, self._ws_cache, self._last = {}, {}, 1e-4
+        return self._ctx_dev
 
     def __del__(self):
         try:
@@ -269,17 +307,22 @@ class NeRFModel(nn.Module):
         except Exception:
             pass
 
+    _RUNTIME_ATTRS = ("_lib", "_ctx", "_ctx_dev", "_packed", "_ws_cache", "_shards", "_last")
+
     def __getstate__(self):
         """torch.save(model) as the reference does (nerf.py:491): drop the library handle, context and scratch."""
         st = dict(self.__dict__)
-        for k in ("_lib", "_ctx", "_ctx_dev", "_packed", "_ws_cache"):
+        for k in self._RUNTIME_ATTRS:
             st.pop(k, None)
         return st
 
     def __setstate__(self, st):
+        """Also accepts the state of a whole-module pickle written by the reference itself (nerf.py:491): it has no
+        `precision` / `check_range`, and its Network has no flat buffer yet."""
         self.__dict__.update(st)
-        self._lib = _lib.load()
-        self._ctx, self._packed, self._ws_cache = None, None, {}
+        self.__dict__.setdefault("precision", os.environ.get("NERF_TINY_PRECISION", DEFAULT_PRECISION))
+        self.__dict__.setdefault("check_range", True)
+        self._init_runtime()
         self.network._flatten()
 
     @property
@@ -288,14 +331,14 @@ class NeRFModel(nn.Module):
 
     @property
     def _prec_train(self):
-        return PRECISION[self.precision]
+        return TRAIN_PRECISION[self.precision]
 
     @property
     def launch_count(self):
         return int(self._lib.nt_launch_count(self._ctx)) if self._ctx is not None else 0
 
-    def _workspace(self, n, train):
-        need = self._lib.nt_render_workspace_bytes(self._ctx, self._prec, n, 1 if train else 0)
+    def _workspace(self, n, train, prec):
+        need = self._lib.nt_render_workspace_bytes(self._ctx, prec, n, 1 if train else 0)
         if train:   # owned by the autograd node
             return torch.empty(need, dtype=torch.uint8, device=self._ctx_dev)
         ws = self._ws_cache.get("render")
@@ -304,30 +347,61 @@ class NeRFModel(nn.Module):
             self._ws_cache["render"] = ws
         return ws
 
-    def _pack(self, flat):
-        if self._prec == _lib.PREC_BF16:
-            _lib.check(self._lib.nt_pack_weights(self._ctx, self._prec, _ptr(flat), _ptr(self._packed), _stream()))
+    def _pack(self, flat, prec):
+        """fp32 flat parameters -> the packed operand image of `prec` (bf16 / fp16 / split fp16); None for fp32."""
+        if prec == _lib.PREC_FP32:
+            return None
+        buf = self._packed.get(prec)
+        if buf is None:
+            buf = torch.empty(max(256, self._lib.nt_packed_weight_bytes(self._ctx, prec)), dtype=torch.uint8,
+                              device=self._ctx_dev)
+            self._packed[prec] = buf
+        _lib.check(self._lib.nt_pack_weights(self._ctx, prec, _ptr(flat), _ptr(buf), _stream(self._ctx_dev)))
+        return buf
+
+    def _set_last(self, last):
+        last = float(last)
+        if last != self._last:
+            bits = int(np.float32(last).view(np.int32))
+            _lib.check(self._lib.nt_set_option(self._ctx, _lib.OPT_LAST_DELTA, bits))
+            self._last = last
+
+    def _globals(self, shard, near, far):
+        """-> (any_step_zero argument, delta0 device tensor or None) for nt_render_forward / nt_render_backward."""
+        if shard is None:
+            return -1, None
+        if isinstance(shard, dict):
+            d0 = shard["delta0"]
+            d0 = d0 if torch.is_tensor(d0) else torch.tensor([float(d0)], dtype=torch.float32)
+            return int(bool(shard["any_step_zero"])), d0.to(self._ctx_dev, torch.float32).reshape(-1).contiguous()
+        if isinstance(shard, tuple):
+            from . import dist as D
+            key = tuple(shard)
+            if key not in self._shards:
+                self._shards[key] = D.ShardGlobals(*key)
+            shard = self._shards[key]
+        return _lib.ANY_STEP_ZERO_DEVICE, shard.compute(self, near, far)
 
     def _render_raw(self, flat, row, col, pose17, kinv, near, far, train, any_step_zero=-1, delta0=None):
         n = row.shape[0]
         dev = self._ctx_dev
+        prec = self._prec_train if train else self._prec
         cc = torch.empty(n, 3, dtype=torch.float32, device=dev)
         cf = torch.empty(n, 3, dtype=torch.float32, device=dev)
-        ws = self._workspace(n, train)
-        self._pack(flat)
+        ws = self._workspace(n, train, prec)
+        packed = self._pack(flat, prec)
         stride = 17 if pose17.shape[-1] == 17 else pose17[0].numel()
-        _lib.check(self._lib.nt_render_forward(self._ctx, self._prec, n, _ptr(row), _ptr(col), _ptr(pose17), stride,
-                                               _ptr(kinv), _ptr(near), _ptr(far), _ptr(flat), _ptr(self._packed),
+        _lib.check(self._lib.nt_render_forward(self._ctx, prec, n, _ptr(row), _ptr(col), _ptr(pose17), stride,
+                                               _ptr(kinv), _ptr(near), _ptr(far), _ptr(flat), _ptr(packed),
                                                any_step_zero, _ptr(delta0), _ptr(cc), _ptr(cf), _ptr(ws), ws.numel(),
-                                               1 if train else 0, _stream()))
+                                               1 if train else 0, _stream(dev)))
         return cc, cf, ws
 
     # -- reference methods -----------------------------------------------------------------------------
-    def render_rays(self, batch_hor, batch_ver, trans_mat, K_inv, near, far, last=0.0001):
+    def render_rays(self, batch_hor, batch_ver, trans_mat, K_inv, near, far, last=0.0001, shard=None):
         """nerf.py:286-323.  trans_mat [N,4,4] (or fp32 pose rows [N,17]); near/far [N]."""
         dev = self._ensure_ctx()
-        if last != 0.0001:
-            raise _lib.NerfTinyError("render_rays: `last` is fixed at 1e-4 in the fused driver (nerf.py:286)")
+        self._set_last(last)
         row = batch_hor.to(dev, non_blocking=True).to(torch.int64).contiguous()
         col = batch_ver.to(dev, non_blocking=True).to(torch.int64).contiguous()
         pose = _dev_f32(trans_mat, dev)
@@ -335,29 +409,31 @@ class NeRFModel(nn.Module):
         near = _dev_f32(near, dev)
         far = _dev_f32(far, dev)
         flat = self.network.flat_params()
+        asz, d0 = self._globals(shard, near, far)
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.network.parameters())
         if needs_grad:
-            cc, cf = _RenderFn.apply(self, _FlatView.apply(flat, *self.network.parameters()), row, col, pose, kinv, near, far)
+            cc, cf = _RenderFn.apply(self, _FlatView.apply(flat, *self.network.parameters()), row, col, pose, kinv, near, far,
+                                     asz, d0)
         else:
-            cc, cf, _ = self._render_raw(flat, row, col, pose, kinv, near, far, train=False)
+            cc, cf, _ = self._render_raw(flat, row, col, pose, kinv, near, far, train=False, any_step_zero=asz, delta0=d0)
         if self.check_range:
-            _lib.check(self._lib.nt_check_status(self._ctx, _stream()))
+            _lib.check(self._lib.nt_check_status(self._ctx, _stream(dev)))
         return cc, cf
 
-    def forward(self, row, column, poses_bound, K_inv):
+    def forward(self, row, column, poses_bound, K_inv, shard=None):
         """nerf.py:333-348: row/column int64 [N] and poses_bound float64 [N,17] arrive on the CPU from the loader."""
         dev = self._ensure_ctx()
         pb = poses_bound.to(dev, non_blocking=True).to(torch.float32).contiguous()   # nerf.py:338
         near = pb[:, 15].contiguous()
         far = pb[:, 16].contiguous()
-        return self.render_rays(row, column, pb, K_inv, near, far)
+        return self.render_rays(row, column, pb, K_inv, near, far, shard=shard)
 
     def ray_loss(self, C_coarse, C_fine, C_true):
         """nerf.py:325-331.  Differentiable (autograd seeds 2(C-Ct) for the render node)."""
         return _RayLossFn.apply(self, C_coarse, C_fine, C_true.to(C_coarse.device, torch.float32))
 
     def check_status(self):
-        _lib.check(self._lib.nt_check_status(self._ctx, _stream()))
+        _lib.check(self._lib.nt_check_status(self._ctx, _stream(self._ctx_dev)))
 
     def set_detach_t_fine(self, on: bool):
         """Diagnostic (NT_OPT_DETACH_T_FINE): treat t_fine as a constant in backward.  The reference does not."""
@@ -378,15 +454,15 @@ class NeRFModel(nn.Module):
         denc = torch.empty(n, 24, device=dev)
         stride = 17 if pose.shape[-1] == 17 else pose[0].numel()
         _lib.check(self._lib.nt_raygen(self._ctx, n, _ptr(row), _ptr(col), _ptr(pose), stride, _ptr(kinv), _ptr(rays), None,
-                                       _ptr(denc), _stream()))
+                                       _ptr(denc), _stream(dev)))
         rgb = torch.empty(n, num_points, 3, device=dev)
         sigma = torch.empty(n, num_points, 1, device=dev)
         flat = self.network.flat_params()
-        self._pack(flat)
+        packed = self._pack(flat, self._prec)
         need = self._lib.nt_mlp_workspace_bytes(self._ctx, self._prec, n, num_points, 0)
         ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
         _lib.check(self._lib.nt_mlp_forward(self._ctx, self._prec, n, num_points, _ptr(t), _ptr(rays), _ptr(denc), _ptr(flat),
-                                            _ptr(self._packed), _ptr(rgb), _ptr(sigma), _ptr(ws), ws.numel(), 0, _stream()))
+                                            _ptr(packed), _ptr(rgb), _ptr(sigma), _ptr(ws), ws.numel(), 0, _stream(dev)))
         return rgb, sigma
 
     def get_density(self, delta, sigma):
@@ -397,7 +473,7 @@ class NeRFModel(nn.Module):
             s_ = s_.squeeze(-1).contiguous()
         n, p = d.shape
         w = torch.empty(n, p, dtype=torch.float32, device=dev)
-        _lib.check(self._lib.nt_get_density(self._ctx, n, p, _ptr(d), _ptr(s_), _ptr(w), _stream()))
+        _lib.check(self._lib.nt_get_density(self._ctx, n, p, _ptr(d), _ptr(s_), _ptr(w), _stream(dev)))
         return w
 
     def color_cum(self, density, color):
@@ -406,7 +482,7 @@ class NeRFModel(nn.Module):
         w, c = _dev_f32(density, dev), _dev_f32(color, dev)
         n, p = w.shape
         out = torch.empty(n, 3, dtype=torch.float32, device=dev)
-        _lib.check(self._lib.nt_color_cum(self._ctx, n, p, _ptr(w), _ptr(c), _ptr(out), _stream()))
+        _lib.check(self._lib.nt_color_cum(self._ctx, n, p, _ptr(w), _ptr(c), _ptr(out), _stream(dev)))
         return out
 
     def resample(self, t_coarse, dense_coarse):
@@ -415,7 +491,7 @@ class NeRFModel(nn.Module):
         t = _dev_f32(t_coarse, dev)
         w = _dev_f32(dense_coarse, dev)
         out = torch.empty(t.shape[0], self.num_fine, device=dev)
-        _lib.check(self._lib.nt_sample_pdf(self._ctx, t.shape[0], _ptr(t), _ptr(w), None, _ptr(out), None, _stream()))
+        _lib.check(self._lib.nt_sample_pdf(self._ctx, t.shape[0], _ptr(t), _ptr(w), None, _ptr(out), None, _stream(dev)))
         self.check_status()
         return out
 
@@ -447,7 +523,7 @@ class _RayLossFn(torch.autograd.Function):
         g_cf = torch.empty_like(cf)
         cc, cf, ct = cc.contiguous(), cf.contiguous(), ct.contiguous()
         _lib.check(model._lib.nt_ray_loss(model._ctx, n, _ptr(cc), _ptr(cf), _ptr(ct), _ptr(loss), _ptr(g_cc), _ptr(g_cf),
-                                          _stream()))
+                                          _stream(cc.device)))
         ctx.save_for_backward(g_cc, g_cf)
         return loss[0]
 
@@ -508,12 +584,12 @@ class FusedAdam(torch.optim.Optimizer):
             peer.barrier()
             _lib.check(model._lib.nt_adam_step_allreduce(model._ctx, flat.numel(), _ptr(flat), arr, peer.world, _ptr(self.m),
                                                          _ptr(self.v), float(g["lr"]), g["betas"][0], g["betas"][1], g["eps"],
-                                                         self.step_count, 1.0, None, _stream()))
+                                                         self.step_count, 1.0, None, _stream(flat.device)))
             peer.barrier()
             return
         _lib.check(model._lib.nt_adam_step(model._ctx, flat.numel(), _ptr(flat), _ptr(grad), _ptr(self.m), _ptr(self.v),
                                            float(g["lr"]), g["betas"][0], g["betas"][1], g["eps"], self.step_count, 1.0,
-                                           _stream()))
+                                           _stream(flat.device)))
 
     def state_dict(self):
         sd = super().state_dict()
@@ -528,10 +604,10 @@ class FusedAdam(torch.optim.Optimizer):
 
 
 def train_step(model: NeRFModel, optimizer: FusedAdam, row, column, pix_val, poses_bound, K_inv,
-               grad_allreduce=None):
+               grad_allreduce=None, shard=None):
     """One iteration of the reference loop body nerf.py:464-475 without autograd bookkeeping:
     forward(train) -> ray_loss -> backward -> [all-reduce] -> fused Adam.  Returns (loss, C_coarse, C_fine)
-    as device tensors (no host sync)."""
+    as device tensors (no host sync).  `shard`: see NeRFModel (this rank's slice of a ray-sharded batch)."""
     dev = model._ensure_ctx()
     L = model._lib
     n = row.shape[0]
@@ -543,13 +619,15 @@ def train_step(model: NeRFModel, optimizer: FusedAdam, row, column, pix_val, pos
     near, far = pb[:, 15].contiguous(), pb[:, 16].contiguous()
     net = model.network
     flat, grads = net.flat_params(), net.flat_grads()
+    asz, d0 = model._globals(shard, near, far)
     grads.zero_()                                                     # optimizer.zero_grad() (nerf.py:467)
-    cc, cf, ws = model._render_raw(flat, rowd, cold, pb, kinv, near, far, train=True)     # nerf.py:470
+    cc, cf, ws = model._render_raw(flat, rowd, cold, pb, kinv, near, far, train=True, any_step_zero=asz, delta0=d0)  # :470
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     g_cc, g_cf = torch.empty_like(cc), torch.empty_like(cf)
-    _lib.check(L.nt_ray_loss(model._ctx, n, _ptr(cc), _ptr(cf), _ptr(ct), _ptr(loss), _ptr(g_cc), _ptr(g_cf), _stream()))
-    _lib.check(L.nt_render_backward(model._ctx, model._prec_train, n, _ptr(near), _ptr(far), _ptr(flat), _ptr(model._packed),
-                                    None, _ptr(g_cc), _ptr(g_cf), _ptr(grads), _ptr(ws), ws.numel(), _stream()))
+    prec = model._prec_train
+    _lib.check(L.nt_ray_loss(model._ctx, n, _ptr(cc), _ptr(cf), _ptr(ct), _ptr(loss), _ptr(g_cc), _ptr(g_cf), _stream(dev)))
+    _lib.check(L.nt_render_backward(model._ctx, prec, n, _ptr(near), _ptr(far), _ptr(flat), _ptr(model._packed.get(prec)),
+                                    _ptr(d0), _ptr(g_cc), _ptr(g_cf), _ptr(grads), _ptr(ws), ws.numel(), _stream(dev)))
     if grad_allreduce is not None and getattr(optimizer, "peer", None) is None:
         grad_allreduce(grads)                                         # NCCL SUM all-reduce of the flat gradient
     optimizer.step()                                                  # nerf.py:474 (fused with the all-reduce if peer)
@@ -559,46 +637,62 @@ def train_step(model: NeRFModel, optimizer: FusedAdam, row, column, pix_val, pos
 class GraphedTrainStep:
     """`train_step` for a fixed batch size with the forward / loss / backward launches (~45 kernels, most of them a few
     microseconds) captured ONCE into a CUDA graph and replayed: the inputs are copied into static device buffers, the
-    fused Adam - whose step count and learning rate change every iteration - and the multi-GPU gradient exchange stay
-    ordinary launches after the replay.  Same arithmetic, same kernels, same order as `train_step`."""
+    fused Adam - whose step count and learning rate change every iteration - and the multi-GPU exchanges (the 16-byte
+    shard-globals reduction before the replay, the gradient exchange after it) stay ordinary launches.  Same arithmetic,
+    same kernels, same order as `train_step`.  The graph is re-captured if the parameter / gradient buffers it was
+    recorded on have been replaced since (Network._flatten, FusedAdam.enable_peer_allreduce)."""
 
-    def __init__(self, model: NeRFModel, optimizer: FusedAdam, n_rays: int, K_inv):
+    def __init__(self, model: NeRFModel, optimizer: FusedAdam, n_rays: int, K_inv, shard=None):
         dev = model._ensure_ctx()
-        self.model, self.opt, self.n = model, optimizer, int(n_rays)
+        self.model, self.opt, self.n, self.shard = model, optimizer, int(n_rays), shard
         self.row = torch.zeros(self.n, dtype=torch.int64, device=dev)
         self.col = torch.zeros(self.n, dtype=torch.int64, device=dev)
         self.pix = torch.zeros(self.n, 3, dtype=torch.float32, device=dev)
         self.pb = torch.zeros(self.n, 17, dtype=torch.float32, device=dev)
+        self.near = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.far = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.kinv = _dev_f32(K_inv, dev)
+        # batch-global quantities of a sharded batch live in a static buffer the captured kernels read
+        self.g = torch.zeros(4, dtype=torch.float32, device=dev) if shard is not None else None
         self.graph = None
         self.out = None
+        self._key = None
+
+    def _buffers_key(self):
+        net = self.model.network
+        return (net.flat_params().data_ptr(), net.flat_grads().data_ptr())
 
     def _body(self):
         model, L = self.model, self.model._lib
         net = model.network
+        dev = self.row.device
         flat, grads = net.flat_params(), net.flat_grads()
-        near, far = self.pb[:, 15].contiguous(), self.pb[:, 16].contiguous()
+        asz = _lib.ANY_STEP_ZERO_DEVICE if self.g is not None else -1
         grads.zero_()
-        cc, cf, ws = model._render_raw(flat, self.row, self.col, self.pb, self.kinv, near, far, train=True)
-        loss = torch.empty(1, dtype=torch.float32, device=flat.device)
+        cc, cf, ws = model._render_raw(flat, self.row, self.col, self.pb, self.kinv, self.near, self.far, train=True,
+                                       any_step_zero=asz, delta0=self.g)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
         g_cc, g_cf = torch.empty_like(cc), torch.empty_like(cf)
+        prec = model._prec_train
         _lib.check(L.nt_ray_loss(model._ctx, self.n, _ptr(cc), _ptr(cf), _ptr(self.pix), _ptr(loss), _ptr(g_cc), _ptr(g_cf),
-                                 _stream()))
-        _lib.check(L.nt_render_backward(model._ctx, model._prec_train, self.n, _ptr(near), _ptr(far), _ptr(flat),
-                                        _ptr(model._packed), None, _ptr(g_cc), _ptr(g_cf), _ptr(grads), _ptr(ws),
-                                        ws.numel(), _stream()))
-        return loss, cc, cf, (near, far, ws, g_cc, g_cf)
+                                 _stream(dev)))
+        _lib.check(L.nt_render_backward(model._ctx, prec, self.n, _ptr(self.near), _ptr(self.far), _ptr(flat),
+                                        _ptr(model._packed.get(prec)), _ptr(self.g), _ptr(g_cc), _ptr(g_cf), _ptr(grads),
+                                        _ptr(ws), ws.numel(), _stream(dev)))
+        return loss, cc, cf, (ws, g_cc, g_cf)
 
     def _capture(self):
-        side = torch.cuda.Stream(device=self.row.device)
-        side.wait_stream(torch.cuda.current_stream())
+        dev = self.row.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                 # eager warm-up: one-time attribute / table setup inside the library
             self._body()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = self._body()
+        self._key = self._buffers_key()
 
     def __call__(self, row, column, pix_val, poses_bound, grad_allreduce=None):
         if row.shape[0] != self.n:
@@ -607,13 +701,64 @@ class GraphedTrainStep:
         self.col.copy_(column, non_blocking=True)
         self.pix.copy_(pix_val, non_blocking=True)
         self.pb.copy_(poses_bound, non_blocking=True)      # float64 loader rows are converted by the copy (nerf.py:338)
-        if self.graph is None:
+        self.near.copy_(self.pb[:, 15])
+        self.far.copy_(self.pb[:, 16])
+        if self.g is not None:
+            _, g = self.model._globals(self.shard, self.near, self.far)
+            self.g.copy_(g)
+        if self.graph is None or self._key != self._buffers_key():
             self._capture()
         self.graph.replay()
         if grad_allreduce is not None and getattr(self.opt, "peer", None) is None:
             grad_allreduce(self.model.network.flat_grads())
         self.opt.step()
         return self.out[0], self.out[1], self.out[2]
+
+
+# ----------------------------------------------------------------------------------------------------
+# Checkpoint files (nerf.py:491 / :410): whole-module pickles that both this module and the reference can read.
+# ----------------------------------------------------------------------------------------------------
+_REF_CLASSES = ("NeRFModel", "Network", "Encoder", "Activation")
+
+
+class _RefPickler(_pickle._Pickler):
+    """Records this module's classes under the reference's module name (`nerf`)."""
+
+    def save_global(self, obj, name=None):
+        if isinstance(obj, type) and obj.__module__ == __name__ and obj.__name__ in _REF_CLASSES:
+            self.write(b"c" + b"nerf\n" + obj.__name__.encode() + b"\n")     # GLOBAL opcode: module `nerf`
+            self.memoize(obj)
+            return
+        return super().save_global(obj, name)
+
+    dispatch = dict(_pickle._Pickler.dispatch)
+    dispatch[type] = save_global
+
+
+class _RefUnpickler(_pickle._Unpickler):
+    """Resolves `nerf.*` / `__main__.*` class references of reference-written files to the classes here."""
+
+    def find_class(self, mod_name, name):
+        if mod_name in ("nerf", "__main__", "ref_nerf") and name in _REF_CLASSES:   # ref_nerf: the name the test harness imports the reference under
+            return globals()[name]
+        return super().find_class(mod_name, name)
+
+
+class _RefPickle:
+    """pickle_module for torch.save / torch.load."""
+    __name__ = "nerf_tiny_b200.nerf._RefPickle"
+    HIGHEST_PROTOCOL, DEFAULT_PROTOCOL = _pickle.HIGHEST_PROTOCOL, _pickle.DEFAULT_PROTOCOL
+    PickleError, PicklingError, UnpicklingError = _pickle.PickleError, _pickle.PicklingError, _pickle.UnpicklingError
+    load, loads, dump, dumps = _pickle.load, _pickle.loads, _pickle.dump, _pickle.dumps
+    Pickler, Unpickler = _RefPickler, _RefUnpickler
+
+
+def save_checkpoint(model, path):
+    torch.save(model, path, pickle_module=_RefPickle)
+
+
+def load_checkpoint(path):
+    return torch.load(path, map_location="cpu", weights_only=False, pickle_module=_RefPickle)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -639,20 +784,23 @@ class NeRFRunner():
         self.model = NeRFModel(num_coarse=n_coarse, num_fine=n_fine, batch_ray=batch_ray, precision=precision).to(device)
         self.results_path, self.ckpt_path, self.low_res = results_path, ckpt_path, low_res
         self.total_iter, self.batch_ray, self.step, self.decay_end = total_iter, batch_ray, step, decay_end
-        # resume: newest "<ckpt_path>*_<iter>.pkl" (nerf.py:404-415); both the reference's whole-module pickles and our
-        # {"model": state_dict, "optimizer": ..., "iter": ...} dictionaries are accepted
+        # resume: newest "<ckpt_path>*_<iter>.pkl" (nerf.py:404-415).  Accepted: whole-module pickles written by this runner
+        # OR by the reference itself (torch.save(self.model), nerf.py:491 - its `nerf.*` classes are mapped onto ours), and
+        # the {"model": state_dict, ...} dictionaries an earlier version of this runner wrote.
         last_iter, opt_state = -1, None
         ck_list = glob.glob(ckpt_path + "*.pkl")
         if continue_ is True and ck_list:
             best = max(ck_list, key=lambda f: int(f.split("_")[-1][:-4]))
             last_iter = int(best.split("_")[-1][:-4])
             print("Last iter:", last_iter)
-            blob = torch.load(best, map_location="cpu", weights_only=False)
+            blob = load_checkpoint(best)
             if isinstance(blob, dict) and "model" in blob:
                 self.model.load_state_dict(blob["model"])
                 opt_state = blob.get("optimizer")
             else:
                 self.model.load_state_dict(blob.state_dict())
+            if opt_state is None and os.path.exists(best[:-4] + ".opt"):
+                opt_state = torch.load(best[:-4] + ".opt", map_location="cpu", weights_only=False)
             self.model = self.model.to(device)
         else:
             print("New running created.")
@@ -692,12 +840,14 @@ class NeRFRunner():
         self.losses = []
 
     def save_checkpoint(self, it):
-        """nerf.py:491 wrote torch.save(self.model); we store the state_dict (reference keys) AND the Adam moments the
-        reference forgot, under the same '<ckpt_path><start_time>_<iter>.pkl' name the resume logic looks for."""
+        """nerf.py:491: torch.save(self.model) under '<ckpt_path><start_time>_<iter>.pkl' - the SAME on-disk format, a
+        whole-module pickle whose classes are recorded as `nerf.NeRFModel / Network / Encoder / Activation`, so the
+        reference's own resume (`torch.load(last_ckpt).to(device)`, nerf.py:410) reads it.  The Adam moments the reference
+        forgot go into a sidecar '<...>_<iter>.opt' that its '*.pkl' glob ignores."""
         os.makedirs(os.path.dirname(self.ckpt_path) or ".", exist_ok=True)
         path = self.ckpt_path + self.start_time + "_" + str(it) + ".pkl"
-        sd = {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}
-        torch.save({"model": sd, "optimizer": self.optimizer.state_dict(), "iter": it}, path)
+        save_checkpoint(self.model, path)
+        torch.save(self.optimizer.state_dict(), path[:-4] + ".opt")
         return path
 
     def _flush_losses(self, it):
@@ -725,7 +875,7 @@ class NeRFRunner():
         while it < self.total_iter:
             n_seen = 0
             for (row, column, pix_val, poses_bound, pic) in dataloader:
-                if row.shape[0] == self.batch_ray and self.model.precision == "bf16":   # fixed-size batches: graph replay
+                if row.shape[0] == self.batch_ray and self.model._prec_train == _lib.PREC_BF16:   # fixed-size batches: graph replay
                     if getattr(self, "_graphed", None) is None:
                         self._graphed = GraphedTrainStep(self.model, self.optimizer, self.batch_ray, self.K_inv)
                     loss, _, _ = self._graphed(row, column, pix_val, poses_bound)

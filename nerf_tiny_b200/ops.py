@@ -16,8 +16,8 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _st():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _st(dev=None):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 class Context:
@@ -63,6 +63,18 @@ class Context:
         t = self._f(n, self.nc)
         _lib.check(self.lib.nt_sample_coarse(self.h, n, _p(near), _p(far), any_step_zero, _p(t), _st()))
         return t
+
+    def shard_globals_local(self, near, far, first_shard):
+        """[flag, delta0 candidate if flag == 0, candidate if flag == 1, 0] of this shard."""
+        g = self._f(4)
+        n = near.shape[0]
+        _lib.check(self.lib.nt_shard_globals_local(self.h, n, _p(near) if n else C.c_void_p(0), _p(far) if n else C.c_void_p(0),
+                                                   1 if first_shard else 0, _p(g), _st()))
+        return g
+
+    def shard_globals_resolve(self, g):
+        _lib.check(self.lib.nt_shard_globals_resolve(self.h, _p(g), _st()))
+        return g
 
     # ---- MLP ----------------------------------------------------------------------------------------
     def pack(self, flat, precision):

@@ -1,7 +1,8 @@
 """Train the UNMODIFIED reference on the analytic scene (CPU, build container only) and store a
 genuinely-trained weight state + the reference's outputs for a held-out batch.
 
-    python -m oracle.make_trained_golden            (~5 min on 8 vCPU)
+    python -m oracle.make_trained_golden            (~5 min on 8 vCPU)   -> trained64 (250 steps)
+    python -m oracle.make_trained_golden --steps 2500 --name trained2k5 --threads 4      (~1 h)  -> trained2k5
 
 Writes tests/golden/trained_weights_fp16.npz (state_dict rounded to fp16 so the fixture stays ~1 MB; the
 rounded values ARE the fixture's weights — reference and CUDA path both load exactly these) and
@@ -23,8 +24,9 @@ from nerf_tiny_b200 import synth             # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def main(steps=250, n_rays=256, lr=1e-3):
-    torch.set_num_threads(8)
+def main(steps=250, n_rays=256, lr=1e-3, name="trained64", threads=8):
+    torch.set_num_threads(threads)
+    wfile = "trained_weights_fp16.npz" if name == "trained64" else name + "_weights_fp16.npz"
     ref = RH.import_reference()
     h = w = 100
     f = synth.focal_of(w)
@@ -44,10 +46,14 @@ def main(steps=250, n_rays=256, lr=1e-3):
         opt.step()
         losses.append(float(loss))
         psnrs.append(O.psnr(cf.detach(), pix))
+        if it % 500 == 499 and name != "trained64":      # long runs: keep a recoverable snapshot outside the repo history
+            os.makedirs(os.path.join(ROOT, ".scratch"), exist_ok=True)
+            torch.save({k: v.detach().clone() for k, v in model.state_dict().items()},
+                       os.path.join(ROOT, ".scratch", f"{name}_it{it + 1}.pt"))
         if it % 25 == 0:
             print(f"[train-ref] it {it} loss {losses[-1]:.3f} psnr {psnrs[-1]:.2f}", flush=True)
     sd16 = {k: v.detach().half() for k, v in model.state_dict().items()}
-    np.savez_compressed(os.path.join(GOLD, "trained_weights_fp16.npz"), **{k: v.numpy() for k, v in sd16.items()},
+    np.savez_compressed(os.path.join(GOLD, wfile), **{k: v.numpy() for k, v in sd16.items()},
                         __losses=np.array(losses), __psnr=np.array(psnrs))
     sd = {k: v.float() for k, v in sd16.items()}
     # held-out pose (not among the 8 training poses), 64 pixels
@@ -55,9 +61,15 @@ def main(steps=250, n_rays=256, lr=1e-3):
     held[0, :15] = np.concatenate((synth.sphere_pose(0.4, 0.5), np.array([[h], [w], [f]])), axis=1).flatten()
     g2 = torch.Generator().manual_seed(5)
     row, col, pix, pb, pic = synth.random_batch(held, 64, h, w, g2)
-    r = forward_case(ref, "trained64", sd, row, col, pb, k_inv, rgb_tol=5e-6)
+    r = forward_case(ref, name, sd, row, col, pb, k_inv, rgb_tol=5e-6)
     print("sigma range", r["sigma_f"].min(), r["sigma_f"].max(), "psnr(last 25)", np.mean(psnrs[-25:]))
 
 
 if __name__ == "__main__":
-    main()
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=250)
+    ap.add_argument("--name", default="trained64")
+    ap.add_argument("--threads", type=int, default=8)
+    a = ap.parse_args()
+    main(steps=a.steps, name=a.name, threads=a.threads)

@@ -566,9 +566,9 @@ def test_training_psnr_parity(dev, golden_dir, prec):
     assert abs(delta) <= 0.1 + 2 * se
 
 
-@pytest.mark.parametrize("version", [5, 6, 7])
+@pytest.mark.parametrize("version", [5, 7])
 def test_mlp_bf16_schedule_variants(ctx, dev, golden_dir, version):
-    """The three schedules of the fused tcgen05 kernel (lock-step pair / cluster multicast / cta_group::2) agree with the
+    """Both schedules of the fused tcgen05 kernel (lock-step pair / cta_group::2) agree with the
     fp32 CUDA path on a launch large enough to give every CTA several tile pairs, plus a ragged tail."""
     g = load(golden_dir, "fern64")
     flat = flat_of(sd_of("trained64"), dev)

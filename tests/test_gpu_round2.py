@@ -1,0 +1,358 @@
+"""GPU parity tests added in round 2 (all through the C-ABI / the drop-in module, checked against the CPU oracle or the
+reference's golden outputs):
+  * NT_PREC_FP16 (default fast path) and NT_PREC_TC32 (fp32 tolerance on the tensor cores) against the reference goldens;
+  * ray sharding on the CUDA path: sharded == unsharded bit for bit with the device-reduced batch-global quantities,
+    and NOT equal without them (nerf.py:234, :288);
+  * a full cfg1 view (100 x 100 = 10 000 rays, many waves of tiles) against the oracle;
+  * small surface items: Activation.forward, render_rays(last=...), device guard.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["kat8", "lego48", "lego48_trained", "fern64", "fern64_trained", "trained64", "trained2k5"]
+FP32, TC32, BF16, FP16 = 0, 1, 2, 3
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def sd_of(case):
+    if case in ("trained64", "trained2k5"):    # weights the reference itself trained (oracle/make_trained_golden.py), as fp16
+        name = "trained_weights_fp16.npz" if case == "trained64" else case + "_weights_fp16.npz"
+        z = np.load(os.path.join(GOLD, name))
+        return {k: torch.from_numpy(z[k].astype(np.float32)) for k in z.files if not k.startswith("__")}
+    sd = O.init_state_dict(624)
+    return O.trained_like(sd) if case.endswith("trained") else sd
+
+
+def load(case):
+    path = os.path.join(GOLD, case + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(case + " fixture not generated")
+    return np.load(path)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from nerf_tiny_b200 import build, ops
+    build.build()
+    c = ops.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+def cu(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t.to(dtype) if dtype is not None else t
+
+
+def model_of(case, dev, precision):
+    from nerf_tiny_b200 import nerf
+    m = nerf.NeRFModel(64, 128, batch_ray=8, precision=precision)
+    m.load_state_dict(sd_of(case))
+    return m.to(dev)
+
+
+def run_case(case, dev, precision):
+    g = load(case)
+    m = model_of(case, dev, precision)
+    with torch.no_grad():
+        cc, cf = m(torch.from_numpy(g["row"]), torch.from_numpy(g["col"]), torch.from_numpy(g["poses_bound"]),
+                   torch.from_numpy(g["k_inv"]))
+    ec = float(np.abs(cc.cpu().numpy() - g["c_coarse"]).max())
+    ef = float(np.abs(cf.cpu().numpy() - g["c_fine"]).max())
+    print("%s %s max-abs err  C_coarse %.2e  C_fine %.2e" % (case, precision, ec, ef))
+    return ec, ef
+
+
+# ------------------------------------------------------------------------------------------------ precisions
+@pytest.mark.parametrize("case", CASES)
+def test_forward_tc32_matches_reference(dev, case):
+    """north_star fp32 tolerance (rgb within 1e-3) ON THE TENSOR CORES: 3-pass split-fp16 tcgen05 kernel (mlp_tc32.cu)."""
+    ec, ef = run_case(case, dev, "tc32")
+    assert ec <= 1e-3 and ef <= 1e-3
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_forward_fp16_matches_reference(dev, case):
+    """The default fast path (fp16 operands, fp32 accumulate; same kernel and speed as bf16): north_star 16-bit tolerance
+    1e-2 on every fixture, including the synthetic *_trained stress states that bf16 operands miss."""
+    ec, ef = run_case(case, dev, "fp16")
+    assert ec <= 1e-2 and ef <= 1e-2
+
+
+def test_forward_bf16_trained2k5(dev):
+    """bf16 operands on the reference-trained 2 500-step fixture (sigma in the tens-hundreds): the 1e-2 gate."""
+    ec, ef = run_case("trained2k5", dev, "bf16")
+    assert ec <= 1e-2 and ef <= 1e-2
+
+
+def _mlp_inputs(ctx, dev, n_rays):
+    g = load("fern64")
+    reps = (n_rays + 63) // 64
+    row = cu(np.tile(g["row"], reps)[:n_rays], dev)
+    col = cu(np.tile(g["col"], reps)[:n_rays], dev)
+    c2w = cu(np.tile(g["c2w"], (reps, 1, 1))[:n_rays], dev)
+    rays, _, de = ctx.raygen(row, col, c2w, cu(g["k_inv"], dev))
+    t = cu(np.tile(g["t_fine"], (reps, 1))[:n_rays], dev)
+    return t, rays, de
+
+
+@pytest.mark.parametrize("weights", ["trained64", "fern64_trained"])
+@pytest.mark.parametrize("n_rays", [1, 3, 149, 2501])
+def test_mlp_tc32_vs_fp32(ctx, dev, weights, n_rays):
+    """The MLP alone: the split-fp16 tensor-core kernel tracks the fp32 CUDA-core path to fp32 round-off on launches from one
+    partial tile to many waves, and is run-to-run deterministic."""
+    from nerf_tiny_b200.ops import flatten_state_dict
+    flat = flatten_state_dict(sd_of(weights), dev)
+    t, rays, de = _mlp_inputs(ctx, dev, n_rays)
+    r32, s32, _ = ctx.mlp_forward(FP32, t, rays, de, flat)
+    packed = ctx.pack(flat, TC32)
+    r, s, _ = ctx.mlp_forward(TC32, t, rays, de, flat, packed)
+    r2, s2, _ = ctx.mlp_forward(TC32, t, rays, de, flat, packed)
+    torch.cuda.synchronize()
+    assert torch.equal(r, r2) and torch.equal(s, s2)
+    er = float((r32 - r).abs().max())
+    es = float((s32 - s).abs().max() / max(1.0, float(s32.abs().max())))
+    print("tc32 vs fp32  %s n=%d  rgb %.2e  sigma(rel) %.2e" % (weights, n_rays, er, es))
+    assert er <= 2e-5 and es <= 2e-5
+
+
+@pytest.mark.parametrize("n_rays", [1, 5, 149, 2501])
+def test_mlp_fp16_vs_fp32(ctx, dev, n_rays):
+    from nerf_tiny_b200.ops import flatten_state_dict
+    flat = flatten_state_dict(sd_of("trained64"), dev)
+    t, rays, de = _mlp_inputs(ctx, dev, n_rays)
+    r32, s32, _ = ctx.mlp_forward(FP32, t, rays, de, flat)
+    r, s, _ = ctx.mlp_forward(FP16, t, rays, de, flat, ctx.pack(flat, FP16))
+    rb, sb, _ = ctx.mlp_forward(BF16, t, rays, de, flat, ctx.pack(flat, BF16))
+    torch.cuda.synchronize()
+    e16, eb = float((r32 - r).abs().max()), float((r32 - rb).abs().max())
+    s16, sbb = float((s32 - s).abs().max()), float((s32 - sb).abs().max())
+    print("n=%d  rgb err fp16 %.2e bf16 %.2e   sigma err fp16 %.2e bf16 %.2e" % (n_rays, e16, eb, s16, sbb))
+    assert e16 <= 2e-3 and s16 <= 4e-3 * max(1.0, float(s32.abs().max()))
+    if n_rays >= 149:
+        assert e16 < eb and s16 < sbb        # 3 more mantissa bits: strictly closer to fp32 than the bf16 operands
+
+
+def test_rendering_modes_refuse_training(ctx, dev):
+    from nerf_tiny_b200 import _lib
+    from nerf_tiny_b200.ops import flatten_state_dict
+    flat = flatten_state_dict(sd_of("kat8"), dev)
+    t, rays, de = _mlp_inputs(ctx, dev, 2)
+    for prec in (FP16, TC32):
+        with pytest.raises(_lib.NerfTinyError):
+            ctx.mlp_forward(prec, t, rays, de, flat, ctx.pack(flat, prec), train=True)
+
+
+# ------------------------------------------------------------------------------------------------ ray sharding on the CUDA path
+def _shard_setup(dev, precision, n=64):
+    from nerf_tiny_b200 import dist as D
+    g = load("fern64")                      # per-ray near / far (LLFF shape): the globals matter
+    m = model_of("fern64", dev, precision)
+    row, col = torch.from_numpy(g["row"][:n]), torch.from_numpy(g["col"][:n])
+    pb, kinv = torch.from_numpy(g["poses_bound"][:n]).clone(), torch.from_numpy(g["k_inv"])
+    return D, g, m, row, col, pb, kinv
+
+
+def _emulated_shards(D, m, pb, dev, world):
+    """ShardGlobals objects for `world` shards living on ONE GPU: the MAX all-reduce is emulated by maxing the shards' local
+    vectors (the arithmetic NCCL performs), everything else is the production path."""
+    n = pb.shape[0]
+    pbf = pb.to(dev, torch.float32)
+    locs = []
+    for r in range(world):
+        sl = D.shard_slice(n, r, world)
+        locs.append(D.ShardGlobals(r, world, reduce_max=lambda t: None).local(m, pbf[sl, 15].contiguous(), pbf[sl, 16].contiguous()))
+    gmax = torch.stack(locs).max(dim=0).values
+
+    def reduce_max(t):
+        t.copy_(torch.maximum(t, gmax))
+
+    return [D.ShardGlobals(r, world, reduce_max=reduce_max) for r in range(world)]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_render_equals_unsharded(dev, precision, world):
+    D, g, m, row, col, pb, kinv = _shard_setup(dev, precision)
+    n = row.shape[0]
+    with torch.no_grad():
+        cc_ref, cf_ref = m(row, col, pb, kinv)
+        shards = _emulated_shards(D, m, pb, dev, world)
+        cc_s, cf_s, cf_naive = [], [], []
+        for r in range(world):
+            sl = D.shard_slice(n, r, world)
+            a, b = m(row[sl], col[sl], pb[sl], kinv, shard=shards[r])
+            cc_s.append(a)
+            cf_s.append(b)
+            cf_naive.append(m(row[sl], col[sl], pb[sl], kinv)[1])          # a shard that is NOT told the globals
+    assert torch.equal(torch.cat(cc_s), cc_ref)
+    assert torch.equal(torch.cat(cf_s), cf_ref)                              # sharded == unsharded, bit for bit
+    assert not torch.equal(torch.cat(cf_naive), cf_ref)                      # negative check: local ray 0 is the wrong delta0
+    if precision == "fp32":
+        assert float(np.abs(cf_ref.cpu().numpy() - g["c_fine"][:n]).max()) <= 1e-3
+
+
+def test_sharded_globals_step_zero_branch(dev):
+    """A degenerate ray (near == far) in the LAST shard switches numpy's linspace formula for every ray of the batch
+    (nerf.py:288): the device-reduced flag and delta0 equal the oracle's global values."""
+    D, g, m, row, col, pb, kinv = _shard_setup(dev, "fp32", n=10)
+    pb[7, 16] = pb[7, 15]
+    shards = _emulated_shards(D, m, pb, dev, 2)
+    pbf = pb.to(dev, torch.float32)
+    for r in range(2):
+        sl = D.shard_slice(10, r, 2)
+        gl = shards[r].compute(m, pbf[sl, 15].contiguous(), pbf[sl, 16].contiguous()).cpu().numpy()
+        t_ref = O.t_coarse_of(pb[:, 15].float().numpy(), pb[:, 16].float().numpy())
+        assert gl[1] == 1.0
+        assert gl[0] == np.float32(t_ref[0, 1] - t_ref[0, 0])
+    assert D.step_is_zero(pb[:, 15].float().numpy(), pb[:, 16].float().numpy())
+
+
+def test_sharded_train_step_equals_unsharded(dev):
+    """fp32 training path: the sum of two shards' gradients (globals reduced on the device) equals the unsharded batch
+    gradient up to fp32 summation order, the losses add up, and shard-wise C_fine is bit-identical."""
+    from nerf_tiny_b200 import nerf
+    D, g, m, row, col, pb, kinv = _shard_setup(dev, "fp32")
+    n = row.shape[0]
+    pix = torch.rand(n, 3, generator=torch.Generator().manual_seed(2))
+
+    class NoStep:                                             # keep the parameters fixed: compare gradients only
+        peer = None
+
+        def step(self):
+            pass
+
+    loss_ref, _, cf_ref = nerf.train_step(m, NoStep(), row, col, pix, pb, kinv)
+    g_ref = m.network.flat_grads().clone()
+    shards = _emulated_shards(D, m, pb, dev, 2)
+    g_sum, loss_sum, cfs = torch.zeros_like(g_ref), 0.0, []
+    for r in range(2):
+        sl = D.shard_slice(n, r, 2)
+        loss, _, cf = nerf.train_step(m, NoStep(), row[sl], col[sl], pix[sl], pb[sl], kinv, shard=shards[r])
+        g_sum += m.network.flat_grads()
+        loss_sum += float(loss)
+        cfs.append(cf)
+    assert torch.equal(torch.cat(cfs), cf_ref)
+    assert abs(loss_sum - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+    rel = float((g_sum - g_ref).norm() / g_ref.norm())
+    print("sharded gradient vs unsharded: rel %.2e" % rel)
+    assert rel <= 1e-5
+
+
+def test_graphed_train_step_sharded(dev):
+    """GraphedTrainStep with shard=: the captured kernels read the batch-global quantities from a static device buffer that
+    is refreshed before every replay; same loss / gradient as train_step with the same shard."""
+    from nerf_tiny_b200 import nerf
+    D, g, m, row, col, pb, kinv = _shard_setup(dev, "bf16")
+    n = row.shape[0]
+    pix = torch.rand(n, 3, generator=torch.Generator().manual_seed(2))
+
+    class NoStep:
+        peer = None
+
+        def step(self):
+            pass
+
+    shards = _emulated_shards(D, m, pb, dev, 2)
+    sl = D.shard_slice(n, 1, 2)                               # the shard that does NOT own global ray 0
+    loss_a, _, cf_a = nerf.train_step(m, NoStep(), row[sl], col[sl], pix[sl], pb[sl], kinv, shard=shards[1])
+    g_a = m.network.flat_grads().clone()
+    gs = nerf.GraphedTrainStep(m, NoStep(), sl.stop - sl.start, kinv, shard=shards[1])
+    for _ in range(2):
+        loss_b, _, cf_b = gs(row[sl], col[sl], pix[sl], pb[sl])
+    torch.cuda.synchronize()
+    assert torch.equal(cf_a, cf_b)
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-6 * abs(float(loss_a))
+    rel = float((m.network.flat_grads() - g_a).norm() / g_a.norm())
+    assert rel <= 1e-3, rel                                   # fp32 atomics: summation order differs run to run
+
+
+# ------------------------------------------------------------------------------------------------ a full BASELINE config
+@pytest.mark.parametrize("precision,tol", [("tc32", 1e-3), ("fp32", 1e-3), ("fp16", 1e-2), ("bf16", 1e-2)])
+def test_cfg1_full_view_matches_oracle(dev, precision, tol):
+    """BASELINE cfg1: every pixel of a 100 x 100 view (10 000 rays = 15 000 sample tiles: all 148 CTAs, several waves, a
+    ragged tail) in ONE launch against the CPU oracle, coarse and fine."""
+    from nerf_tiny_b200 import nerf, synth
+    h = w = 100
+    f = synth.focal_of(w)
+    rows17 = synth.pose_rows(2, h, w, f)
+    row, col, pix, pb, pic = synth.view_batch(rows17, 1, h, w)
+    k_inv = synth.k_inv_of(h, w, f)
+    sd = sd_of("trained64")
+    ref = _cfg1_oracle(sd, row, col, pb, k_inv)
+    m = nerf.NeRFModel(64, 128, batch_ray=row.shape[0], precision=precision)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    with torch.no_grad():
+        cc, cf = m(row, col, pb, k_inv)
+    ec = float((cc.cpu() - ref[0]).abs().max())
+    ef = float((cf.cpu() - ref[1]).abs().max())
+    print("cfg1 full view %s: C_coarse %.2e C_fine %.2e" % (precision, ec, ef))
+    assert cc.shape == (h * w, 3) and ec <= tol and ef <= tol
+
+
+_CFG1 = {}
+
+
+def _cfg1_oracle(sd, row, col, pb, k_inv):
+    if "ref" not in _CFG1:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        outs = []
+        with torch.no_grad():
+            for lo in range(0, row.shape[0], 2500):          # the oracle's intermediates are [N,P,256] fp32: chunk the view
+                sl = slice(lo, lo + 2500)
+                # chunking changes neither global quantity here: near / far are constant over the view
+                outs.append(O.forward(sd, row[sl].numpy(), col[sl].numpy(), pb[sl], k_inv))
+        _CFG1["ref"] = (torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs]))
+    return _CFG1["ref"]
+
+
+# ------------------------------------------------------------------------------------------------ surface items
+def test_activation_forward():
+    from nerf_tiny_b200 import nerf
+    x = torch.tensor([-2.0, 0.0, 3.5])
+    assert torch.equal(nerf.Activation()(x), torch.abs(x))      # nerf.py:73-74
+
+
+@pytest.mark.parametrize("last", [1e-4, 0.05, 1.0])
+def test_render_rays_last(dev, last):
+    """render_rays(last=...) (nerf.py:286, :311): the delta of the last merged sample."""
+    g = load("lego48_trained")
+    m = model_of("lego48_trained", dev, "fp32")
+    sd = sd_of("lego48_trained")
+    pb = torch.from_numpy(g["poses_bound"]).float()
+    c2w, _, _, _, near, far = O.poses_extract(pb)
+    with torch.no_grad():
+        occ, ocf = O.render_rays(sd, g["row"], g["col"], c2w.numpy(), g["k_inv"], near.numpy(), far.numpy(), last=last)
+        cc, cf = m.render_rays(torch.from_numpy(g["row"]), torch.from_numpy(g["col"]), pb, torch.from_numpy(g["k_inv"]),
+                               near, far, last=last)
+    assert float((cf.cpu() - ocf).abs().max()) <= 1e-3
+    assert float((cc.cpu() - occ).abs().max()) <= 1e-3
+
+
+def test_context_on_second_device_leaves_current_device_alone():
+    """nt_create / every launching entry point run on the CONTEXT's device and restore the caller's."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from nerf_tiny_b200 import nerf
+    torch.cuda.set_device(0)
+    g = load("kat8")
+    m = model_of("kat8", torch.device("cuda", 1), "fp16")
+    with torch.no_grad():
+        cc, cf = m(torch.from_numpy(g["row"]), torch.from_numpy(g["col"]), torch.from_numpy(g["poses_bound"]),
+                   torch.from_numpy(g["k_inv"]))
+    assert torch.cuda.current_device() == 0 and cf.device.index == 1
+    assert float(np.abs(cf.cpu().numpy() - g["c_fine"]).max()) <= 1e-2
