@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the NeRF-tiny per-ray hot path on B200 (see BASELINE.json / SURVEY.md §8(d)).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision fp16|bf16|tc32|fp32]
 
 One "step" = one pass of the hot path over one batch of synthetic input.  Workload at N=1 = BASELINE.json
 configs[1]: lego.ini coarse64+fine128 render of a full 400x400 synthetic Blender-shape view (160 000 rays,
@@ -10,8 +10,11 @@ random-init weights of the reference architecture, synthetic pose).  With N>1 ev
 
 Printed JSON (one line, rank 0): metric/value/unit (device-resident inputs), ms_per_step, e2e (public API,
 host buffers, H2D+D2H inside the timed region), roofline (dominant kernel: the fused tcgen05 encode+MLP),
-cpu_baseline (the oracle port of the reference timed on the host cores), train (the training step, extra),
-clocks, gpu_launches.
+cpu_baseline (the reference's own CPU path - oracle/_ref, else the oracle port - timed on the host cores), clocks,
+gpu_launches, and extra blocks: train / train_4096 (training step with its own roofline), train_cfg4 (BASELINE configs[3]:
+one 4096-ray fern-shape batch ray-sharded over the N ranks, strong scaling), render_cfg5 (configs[4]: 1 048 576 rays of
+800x800 views split over the N ranks INCLUDING the gather to rank 0 and the copy to the host), precisions (the MLP kernel
+of every precision mode at the fine-pass shape).
 """
 from __future__ import annotations
 
@@ -98,23 +101,47 @@ def view_inputs(rank, height=H, width=W):
 
 
 # --------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the reference's CPU PyTorch path on the host cores
+# reference arm / cpu_baseline: the reference's own CPU PyTorch path on the host cores.  The UNMODIFIED reference module
+# (staged into oracle/_ref/ at build time, see oracle/ref_harness.py) when present, else the oracle port.
 # --------------------------------------------------------------------------------------------------------
-def cpu_render_rays_per_s(n_rays, iters, threads):
+def cpu_render_fn(n_rays, threads):
+    """-> (callable running one no-grad render of `n_rays` strided pixels of the bench view, kind)."""
     from oracle import nerf_oracle as O
+    from oracle import ref_harness as RH
     torch.set_num_threads(threads)
     row, col, pix, pb, k_inv, _ = view_inputs(0)
-    sd = O.init_state_dict(624)
     sel = torch.linspace(0, N_RAYS - 1, n_rays).long()
-    row, col, pb = row[sel], col[sel], pb[sel]
+    row, col, pb = row[sel].contiguous(), col[sel].contiguous(), pb[sel].contiguous()
+    if RH.available():
+        try:
+            ref = RH.import_reference()
+            model = RH.make_model(ref, n_rays, O.init_state_dict(624))
+            model.eval()
+
+            def go_ref():
+                with torch.no_grad():
+                    return model(row, col, pb, k_inv)            # nerf.py:333, unmodified
+            go_ref()
+            return go_ref, "reference"
+        except Exception as e:       # the baseline must never sink the run: fall back to the port, say so
+            print(f"[bench] reference module unusable ({e!r}); timing the oracle port", file=sys.stderr)
+    sd = O.init_state_dict(624)
+
+    def go_port():
+        with torch.no_grad():
+            return O.forward(sd, row.numpy(), col.numpy(), pb, k_inv)
+    return go_port, "port"
+
+
+def cpu_render_rays_per_s(n_rays, iters, threads):
+    go, kind = cpu_render_fn(n_rays, threads)
     times = []
-    with torch.no_grad():
-        for i in range(iters + 1):
-            t0 = time.perf_counter()
-            O.forward(sd, row.numpy(), col.numpy(), pb, k_inv)
-            if i > 0:
-                times.append(time.perf_counter() - t0)
-    return n_rays / float(np.mean(times)), float(np.mean(times))
+    for i in range(iters + 1):
+        t0 = time.perf_counter()
+        go()
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    return n_rays / float(np.mean(times)), float(np.mean(times)), kind
 
 
 def run_reference(args):
@@ -123,27 +150,22 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     n = 2048
-    warm = max(0, min(args.warmup, 1))
-    from oracle import nerf_oracle as O
-    torch.set_num_threads(threads)
-    row, col, pix, pb, k_inv, _ = view_inputs(0)
-    sd = O.init_state_dict(624)
-    sel = torch.linspace(0, N_RAYS - 1, n).long()
-    row, col, pb = row[sel], col[sel], pb[sel]
-    with torch.no_grad():
-        for _ in range(warm):
-            O.forward(sd, row.numpy(), col.numpy(), pb, k_inv)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            O.forward(sd, row.numpy(), col.numpy(), pb, k_inv)
-        dt = time.perf_counter() - t0
+    go, kind = cpu_render_fn(n, threads)
+    for _ in range(args.warmup):
+        go()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        go()
+    dt = time.perf_counter() - t0
     v = n * args.steps / dt
-    sample = f"{n} rays of the view per step (evenly strided pixels), oracle port (torch CPU fp32), {threads} threads"
+    what = "the unmodified reference module (oracle/_ref/nerf.py NeRFModel.forward)" if kind == "reference" else \
+        "oracle port of the reference (torch CPU fp32)"
+    sample = f"{n} rays of the view per step (evenly strided pixels), {what}, {threads} threads"
     out = {"impl": "reference", "metric": "rays/sec (render, coarse64+fine128)", "value": v, "unit": "rays/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * dt / args.steps,
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "sample": sample},
-           "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": kind, "sample": sample},
            "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -239,18 +261,25 @@ def run_b200(args):
         roof_hbm = hbm_rooflines(model, dev, flush, N_RAYS)
 
     # ---- training step (extra): reference loop body nerf.py:464-475 through train_step ------------------
-    train = None
+    train = train4k = cfg4 = cfg5 = precs = None
     if not args.no_train:
         train = bench_train(model, dev, rows17, world, rank, barrier, args)
+        train4k = bench_train(model, dev, rows17, world, rank, barrier, args, batch=4096)
+        cfg4 = bench_train_cfg4(model, dev, world, rank, barrier, args)
+    if not args.no_extra:
+        cfg5 = bench_render_cfg5(model, dev, world, rank, barrier, args)
+        if rank == 0:
+            precs = bench_precisions(model, dev, d_row, d_col, d_pb, d_kinv, flat, flush)
 
     cpu = None
     if rank == 0 and not args.no_cpu:
         try:
             threads = os.cpu_count() or 1
-            v, sec = cpu_render_rays_per_s(1024, 3, threads)
-            cpu = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
-                   "sample": f"3 x 1024 rays of the same view (strided pixels), oracle port of the reference's CPU PyTorch "
-                             f"path, {sec:.2f} s per 1024-ray batch"}
+            v, sec, kind = cpu_render_rays_per_s(1024, 3, threads)
+            cpu = {"value": v, "unit": "rays/s", "cores": threads, "kind": kind,
+                   "sample": f"3 x 1024 rays of the same view (strided pixels), "
+                             f"{'the unmodified reference module' if kind == 'reference' else 'oracle port of the reference'} "
+                             f"(CPU PyTorch fp32), {sec:.2f} s per 1024-ray batch"}
         except Exception as e:  # the baseline must never sink the GPU numbers
             cpu = {"value": None, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
@@ -269,12 +298,28 @@ def run_b200(args):
             "mlp_tc_frac_of_peak": value / world * FLOP_PER_RAY_RENDER / (pk["tf"] * 1e12),
             "e2e": {"value": world * N_RAYS / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "roofline": roof, "roofline_hbm_kernels": roof_hbm, "cpu_baseline": cpu, "train": train, "clocks": clocks,
+            "gpu_launches": launches, "roofline": roof, "roofline_hbm_kernels": roof_hbm, "cpu_baseline": cpu, "train": train, "train_4096": train4k, "train_cfg4": cfg4, "render_cfg5": cfg5,
+            "precisions": precs, "clocks": clocks,
             "peaks": pk,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from profiles/ncu_traffic.json (written by tools/ncu_traffic.py from an
+    `ncu --set full` capture of this bench's own launch); null when no capture of the current kernel is committed."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if kernel and os.path.exists(path):
+        try:
+            rec = json.load(open(path)).get(kernel)
+            if rec:
+                return {"traffic": rec["dram_bytes_read"] + rec["dram_bytes_write"],
+                        "traffic_unit": "B per launch (dram__bytes_read.sum + dram__bytes_write.sum, %s)" % rec.get("source", "ncu")}
+        except Exception:
+            pass
+    return {"traffic": None, "traffic_unit": "no ncu capture committed for this kernel"}
 
 
 def mlp_roofline(model, dev, d_row, d_col, d_pb, d_kinv, flat, flush, iters=5):
@@ -319,9 +364,9 @@ def mlp_roofline(model, dev, d_row, d_col, d_pb, d_kinv, flat, flush, iters=5):
             ("mlp_tc32_kernel (3-pass split-fp16)" if prec == 1 else "gemm_f32_kernel chain (fp32 accuracy path)"), "bound": "tensor", "achieved": ach, "peak": pk["tf"],
             "unit": "TFLOP/s", "frac": ach / pk["tf"], "frac_of_sustained": ach / pk["tf_sustained"] if pk["tf_sustained"] else None,
             "peak_source": pk["src"] + " bf16 burst", "launch_ms": dur * 1e3, "algorithmic_flop_per_launch": flops,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture summarised in
-            # profiles/r1j_mlp_tc7_summary.txt (110.8 MB + 277.2 MB); algorithmic bytes = 4 B t + 16 B rgb/sigma per sample
-            "traffic": 388.0e6 if prec in (2, 3) else None, "traffic_unit": "B per launch (ncu, profiles/r1j_mlp_tc7_summary.txt)"}
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the committed ncu --set full summary of this
+            # kernel (tools/ncu_traffic.py writes it); algorithmic bytes = 4 B t + 16 B rgb/sigma per sample
+            **ncu_traffic("mlp_tc7_kernel" if prec in (2, 3) else ("mlp_tc32_kernel" if prec == 1 else None))}
 
 
 def hbm_rooflines(model, dev, flush, n, iters=5):
@@ -369,23 +414,45 @@ def hbm_rooflines(model, dev, flush, n, iters=5):
     return out
 
 
-def bench_train(model, dev, rows17, world, rank, barrier, args):
+def _max_over_ranks(ms, dev, world):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def _time_steps(one, steps, warm, barrier, dev, world):
+    for i in range(warm):
+        one(i)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        out = one(i)
+    b.record()
+    barrier()
+    return _max_over_ranks(a.elapsed_time(b) / steps, dev, world), out
+
+
+def bench_train(model, dev, rows17, world, rank, barrier, args, batch=TRAIN_BATCH, steps=None):
+    """Weak scaling: every rank trains on its own `batch` rays per step (lego shape), one SUM all-reduce per step."""
     from nerf_tiny_b200 import nerf, synth
     import torch.distributed as dist
     gen = torch.Generator().manual_seed(1000 + rank)
     k_inv = synth.k_inv_of(H, W, synth.focal_of(W))
-    batches = [synth.random_batch(rows17, TRAIN_BATCH, H, W, gen) for _ in range(4)]
+    batches = [synth.random_batch(rows17, batch, H, W, gen) for _ in range(4)]
     opt = nerf.FusedAdam(model, lr=3e-4, betas=(0.9, 0.999), eps=1e-7)
     saved = model.network.flat_params().clone()
     model.train()
     allreduce = (lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)) if world > 1 else None
     # N>1: the SUM all-reduce is fused into the Adam kernel over NVLink peer memory (falls back to NCCL if unavailable)
     fused_ar = opt.enable_peer_allreduce() if world > 1 else False
-    steps, warm = max(2, min(args.steps, 5)), 2
+    steps = steps or max(50, args.steps)
     pinned = [tuple(x.pin_memory() for x in b) for b in batches]
-
     # forward / loss / backward replayed from one CUDA graph (NT_TRAIN_GRAPH=0: launch by launch through train_step)
-    graphed = nerf.GraphedTrainStep(model, opt, TRAIN_BATCH, k_inv) if os.environ.get("NT_TRAIN_GRAPH", "1") != "0" else None
+    graphed = nerf.GraphedTrainStep(model, opt, batch, k_inv) if os.environ.get("NT_TRAIN_GRAPH", "1") != "0" else None
 
     def one(i):
         row, col, pix, pb, pic = pinned[i % len(pinned)]
@@ -394,33 +461,189 @@ def bench_train(model, dev, rows17, world, rank, barrier, args):
         else:
             loss, _, _ = nerf.train_step(model, opt, row, col, pix, pb, k_inv, grad_allreduce=allreduce)
         return loss
-    for i in range(warm):
-        one(i)
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for i in range(steps):
-        loss = one(i)
-    b.record()
-    barrier()
-    ms = a.elapsed_time(b) / steps
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms, loss = _time_steps(one, steps, 5, barrier, dev, world)
+    last_loss = float(loss)                                        # the step's result read back on the host
     model.check_status()
     model.network.flat_params().copy_(saved)
     model.eval()
-    v = world * TRAIN_BATCH / (ms * 1e-3)
+    v = world * batch / (ms * 1e-3)
+    pk = peaks()
+    tf = v / world * FLOP_PER_RAY_TRAIN / 1e12
+    tr = ncu_traffic_train()
     return {"metric": "rays/sec (train step: fwd+bwd+Adam, coarse64+fine128)", "value": v, "unit": "rays/s",
-            "ms_per_step": ms, "rays_per_step_per_gpu": TRAIN_BATCH, "steps": steps,
+            "ms_per_step": ms, "rays_per_step_per_gpu": batch, "steps": steps, "warmup": 5, "scaling": "weak",
             "dtype": "bf16" if args.precision in ("bf16", "fp16") else "f32",
             "note": "fused tcgen05 forward with TMA-stored bf16 stash + fused tcgen05 backward-data chain + one grouped split-K dW launch per pass "
-                    "+ fused Adam; forward/loss/backward replayed as one CUDA graph; host batches, H2D inside the timed region; one SUM all-reduce of the 2.4 MB gradient "
-                    "per step when N>1",
+                    "+ fused Adam; forward/loss/backward replayed as one CUDA graph; host batches in pinned memory, H2D inside the timed "
+                    "region, the loss is read back on the host after the last step; one SUM all-reduce of the 2.4 MB gradient per step when N>1",
+            "e2e": {"h2d_bytes_per_step": batch * (8 + 8 + 12 + 17 * 8), "d2h_bytes_per_step": 4,
+                    "note": "value IS end to end: the public GraphedTrainStep / train_step call with host batches"},
             "grad_exchange": ("fused all-reduce+Adam kernel over NVLink peer memory" if fused_ar else
                               ("NCCL all-reduce" if world > 1 else "none")),
-            "frac_of_tc_peak": v / world * FLOP_PER_RAY_TRAIN / (peaks()["tf"] * 1e12), "last_loss": float(loss)}
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tf / pk["tf"],
+                         "frac_of_sustained": tf / pk["tf_sustained"] if pk["tf_sustained"] else None,
+                         "algorithmic_flop_per_ray": FLOP_PER_RAY_TRAIN, "peak_source": pk["src"] + " bf16 burst", **tr},
+            "frac_of_tc_peak": tf / pk["tf"], "last_loss": last_loss}
+
+
+def ncu_traffic_train():
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        try:
+            rec = json.load(open(path)).get("train_step")
+            if rec:
+                return {"traffic": rec["dram_bytes_per_sample"], "traffic_unit": "DRAM B per sample, all kernels of one step (%s)" % rec.get("source", "ncu")}
+        except Exception:
+            pass
+    return {"traffic": None, "traffic_unit": "no ncu capture committed"}
+
+
+FERN_H, FERN_W, FERN_F, CFG4_BATCH = 378, 504, 407.6, 4096
+
+
+def bench_train_cfg4(model, dev, world, rank, barrier, args):
+    """BASELINE configs[3]: fern.ini LLFF-shape 504x378 rays with per-image near/far, ONE 4096-ray batch per step
+    ray-sharded over the N ranks (strong scaling): every rank trains on its contiguous 4096/N slice with the batch-global
+    quantities reduced on the device, gradients SUM-all-reduced (fused into the Adam kernel over NVLink peer memory)."""
+    from nerf_tiny_b200 import nerf, synth, dist as D
+    import torch.distributed as dist
+    rows17 = synth.pose_rows(20, FERN_H, FERN_W, FERN_F, llff_bounds=True, seed=3)
+    k_inv = synth.k_inv_of(FERN_H, FERN_W, FERN_F)
+    gen = torch.Generator().manual_seed(4040)                     # the SAME global batches on every rank
+    batches = [synth.random_batch(rows17, CFG4_BATCH, FERN_H, FERN_W, gen) for _ in range(4)]
+    sl = D.shard_slice(CFG4_BATCH, rank, world)
+    n_loc = sl.stop - sl.start
+    pinned = [tuple(x[sl].contiguous().pin_memory() for x in b) for b in batches]
+    opt = nerf.FusedAdam(model, lr=3e-4, betas=(0.9, 0.999), eps=1e-7)
+    saved = model.network.flat_params().clone()
+    model.train()
+    allreduce = (lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)) if world > 1 else None
+    fused_ar = opt.enable_peer_allreduce() if world > 1 else False
+    shard = (rank, world) if world > 1 else None
+    graphed = nerf.GraphedTrainStep(model, opt, n_loc, k_inv, shard=shard)
+
+    def one(i):
+        row, col, pix, pb, pic = pinned[i % len(pinned)]
+        return graphed(row, col, pix, pb, grad_allreduce=allreduce)[0]
+    steps = max(50, args.steps)
+    ms, loss = _time_steps(one, steps, 5, barrier, dev, world)
+    last_loss = float(loss)
+    # the exchange's share: the optimiser step alone (N>1: two symmetric-memory barriers + the kernel that sums all ranks'
+    # gradients over NVLink and applies Adam; N=1: the Adam kernel), and the 16-byte MAX all-reduce of the shard globals
+    ms_opt, _ = _time_steps(lambda i: opt.step(), 50, 5, barrier, dev, world)
+    ms_glob = None
+    if world > 1:
+        near, far = graphed.near, graphed.far
+        ms_glob, _ = _time_steps(lambda i: model._globals(shard, near, far), 50, 5, barrier, dev, world)
+    model.check_status()
+    model.network.flat_params().copy_(saved)
+    model.eval()
+    v = CFG4_BATCH / (ms * 1e-3)
+    pk = peaks()
+    tf = v * FLOP_PER_RAY_TRAIN / 1e12 / world
+    return {"metric": "rays/sec (train step, fern 504x378, one 4096-ray batch ray-sharded over N GPUs)", "value": v,
+            "unit": "rays/s", "ms_per_step": ms, "global_batch": CFG4_BATCH, "rays_per_step_per_gpu": n_loc, "steps": steps,
+            "scaling": "strong", "n_gpus": world, "dtype": "bf16",
+            "optimizer_and_exchange_ms": ms_opt, "shard_globals_allreduce_ms": ms_glob,
+            "exchange_share_of_step": (ms_opt + (ms_glob or 0.0)) / ms,
+            "grad_exchange": ("fused all-reduce+Adam kernel over NVLink peer memory" if fused_ar else
+                              ("NCCL all-reduce" if world > 1 else "none")),
+            "frac_of_tc_peak_per_gpu": tf / pk["tf"], "last_loss": last_loss}
+
+
+CFG5_H = CFG5_W = 800
+CFG5_RAYS = 1 << 20
+
+
+def bench_render_cfg5(model, dev, world, rank, barrier, args):
+    """BASELINE configs[4]: 800x800 views, 1 048 576 rays per launch (1.64 views) ray-sharded over the N ranks; the timed
+    step INCLUDES the gather of the (N,3) outputs to every rank (NCCL all-gather over NVLink, 12 B/ray) and rank 0's copy
+    of the assembled image block to pinned host memory."""
+    from nerf_tiny_b200 import synth, dist as D
+    f = synth.focal_of(CFG5_W)
+    rows17 = synth.pose_rows(8, CFG5_H, CFG5_W, f)
+    k_inv = synth.k_inv_of(CFG5_H, CFG5_W, f)
+    idx = np.arange(CFG5_RAYS)
+    pic, rem = idx // (CFG5_H * CFG5_W), idx % (CFG5_H * CFG5_W)
+    sl = D.shard_slice(CFG5_RAYS, rank, world)
+    row = torch.from_numpy((rem // CFG5_W)[sl].astype(np.int64)).to(dev)
+    col = torch.from_numpy((rem % CFG5_W)[sl].astype(np.int64)).to(dev)
+    pb = torch.from_numpy(rows17[pic[sl]]).to(dev).float().contiguous()
+    kinv = k_inv.to(dev)
+    near, far = pb[:, 15].contiguous(), pb[:, 16].contiguous()
+    flat = model.network.flat_params()
+    host = torch.empty(CFG5_RAYS, 3, dtype=torch.float32).pin_memory() if rank == 0 else None
+    shard = (rank, world) if world > 1 else None
+
+    def one(i):
+        with torch.no_grad():
+            asz, d0 = model._globals(shard, near, far)
+            cc, cf, _ = model._render_raw(flat, row, col, pb, kinv, near, far, train=False, any_step_zero=asz, delta0=d0)
+            full = D.gather_rows(cf, CFG5_RAYS)
+            if rank == 0:
+                host.copy_(full, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return cf
+    steps = max(3, min(args.steps, 5))
+    ms, _ = _time_steps(one, steps, 2, barrier, dev, world)
+    model.check_status()
+    v = CFG5_RAYS / (ms * 1e-3)
+    pk = peaks()
+    return {"metric": "rays/sec (render 800x800, 1 048 576 rays per launch ray-sharded over N GPUs, gather + D2H included)",
+            "value": v, "unit": "rays/s", "ms_per_step": ms, "rays_per_launch": CFG5_RAYS, "rays_per_gpu": sl.stop - sl.start,
+            "steps": steps, "scaling": "strong", "n_gpus": world, "dtype": DTYPE[args.precision],
+            "d2h_bytes_per_step": CFG5_RAYS * 12, "gather_bytes_per_rank": (CFG5_RAYS * 12) if world > 1 else 0,
+            "frac_of_tc_peak_per_gpu": v / world * FLOP_PER_RAY_RENDER / (pk["tf"] * 1e12)}
+
+
+def bench_precisions(model, dev, d_row, d_col, d_pb, d_kinv, flat, flush):
+    """The encode+MLP kernel of every precision mode alone at the fine-pass shape of the workload (160 000 x 128 samples):
+    the fp32-tolerance mode on the tensor cores (tc32, 3 MMAs per product: its roofline is a third of the 16-bit peak) next to
+    the CUDA-core fp32 path it replaces, and bf16 next to fp16 (same kernel, same speed)."""
+    from nerf_tiny_b200 import _lib, nerf
+    import ctypes as C
+    L, h = model._lib, model._ctx
+    n = d_row.shape[0]
+    rays, denc = torch.empty(n, 16, device=dev), torch.empty(n, 24, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.nt_raygen(h, n, p(d_row), p(d_col), p(d_pb), 17, p(d_kinv), p(rays), None, p(denc), st))
+    t = (torch.rand(n, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(3)) * 4 + 2).contiguous()
+    rgb, sig = torch.empty(n, 128, 3, device=dev), torch.empty(n, 128, device=dev)
+    pk = peaks()
+    out, ref = [], None
+    for name in ("fp32", "tc32", "fp16", "bf16"):
+        prec = nerf.PRECISION[name]
+        packed = model._pack(flat, prec)
+        ws = torch.empty(max(256, L.nt_mlp_workspace_bytes(h, prec, n, 128, 0)), dtype=torch.uint8, device=dev)
+        go = lambda: _lib.check(L.nt_mlp_forward(h, prec, n, 128, p(t), p(rays), p(denc), p(flat), p(packed), p(rgb), p(sig),
+                                                 p(ws), ws.numel(), 0, st))
+        iters = 1 if name == "fp32" else 3
+        go()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            go()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        dur = float(np.mean(ms)) * 1e-3
+        if name == "fp32":
+            ref = (rgb.clone(), sig.clone())
+        err_rgb = float((rgb - ref[0]).abs().max())
+        err_sig = float((sig - ref[1]).abs().max() / ref[1].abs().max())
+        ach = FLOP_PER_SAMPLE * n * 128 / dur / 1e12
+        mma_per_product = {"fp32": None, "tc32": 3, "fp16": 1, "bf16": 1}[name]
+        peak = pk["tf"] / mma_per_product if mma_per_product else None
+        out.append({"precision": name, "kernel": {"fp32": "gemm_f32_kernel chain (CUDA cores)", "tc32": "mlp_tc32_kernel (tcgen05, 3-pass split fp16)",
+                                                  "fp16": "mlp_tc7_kernel<fp16> (tcgen05 cta_group::2)", "bf16": "mlp_tc7_kernel<bf16> (tcgen05 cta_group::2)"}[name],
+                    "launch_ms": dur * 1e3, "samples_per_s": n * 128 / dur, "useful_tflops": ach,
+                    "roofline_peak_tflops": peak, "frac": ach / peak if peak else None,
+                    "max_abs_rgb_vs_fp32": err_rgb, "max_rel_sigma_vs_fp32": err_sig})
+    return out
 
 
 def main():
@@ -432,6 +655,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "tc32", "fp32"])
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg5 render sweep and the precision table")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -17,9 +17,17 @@ import torch.distributed as dist
 f32 = np.float32
 
 
+SHARD_ALIGN = 4      # rays: 4 x 64 coarse samples = 2 x 128 fine samples = one tile PAIR of the fused MLP kernel
+
+
 def shard_slice(n: int, rank: int, world: int) -> slice:
-    """Contiguous ceil(n/world)-sized slices; the last ranks may get fewer (or zero) rays."""
+    """Contiguous ceil(n/world)-sized slices, rounded up to a multiple of 4 rays; the last ranks may get fewer (or zero)
+    rays.  The alignment keeps every sample in the same half of its 256-sample tile pair as in the unsharded launch: the
+    cta_group::2 MLP kernel accumulates the skip / view K-chunk first for one tile of a pair and last for the other, so a
+    shard boundary in the middle of a pair would change fp32 summation order (last-bit differences) - with aligned
+    boundaries sharded == unsharded bit for bit."""
     per = (n + world - 1) // world
+    per = (per + SHARD_ALIGN - 1) // SHARD_ALIGN * SHARD_ALIGN
     lo = min(n, rank * per)
     return slice(lo, min(n, lo + per))
 

@@ -1,8 +1,12 @@
-"""Import the UNMODIFIED reference (/root/reference/nerf.py) in the build container.
+"""Import the UNMODIFIED reference (nerf.py of D-Hank/NeRF-tiny).
 
-TEST INFRASTRUCTURE ONLY, and only usable where /root/reference exists (the
-build container).  Nothing that runs on the GPU box imports this module: the
-goldens it produces are committed under tests/golden/ by oracle/make_golden.py.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Where it is found:
+  * /root/reference (the build container): used by oracle/make_golden.py & co to produce tests/golden/, and by the CPU
+    tests that cross-check the oracle;
+  * oracle/_ref/ : a byte-for-byte staging copy of nerf.py + loader.py made by `stage()` at build time (git-ignored, so
+    it never enters the history, but it travels to the GPU box with the snapshot like the built .so).  Its only consumer
+    is `bench.py --impl reference` / `cpu_baseline`, which time the reference's own CPU path on the box's host cores.
+The parity tests that run on the GPU box use the committed goldens and the oracle port, never this module.
 
 The reference imports `imageio` and `matplotlib.pyplot` at module scope
 (nerf.py:7, 12); neither is installed here, so empty stub modules are injected
@@ -16,11 +20,37 @@ import types
 
 import torch
 
-REF_DIR = os.environ.get("NERF_TINY_REFERENCE", "/root/reference")
+SRC_DIR = "/root/reference"
+STAGE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _resolve() -> str:
+    env = os.environ.get("NERF_TINY_REFERENCE")
+    if env:
+        return env
+    return SRC_DIR if os.path.isfile(os.path.join(SRC_DIR, "nerf.py")) else STAGE_DIR
+
+
+REF_DIR = _resolve()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REF_DIR, "nerf.py"))
+
+
+def stage() -> bool:
+    """Copy the reference's two modules, unmodified, into oracle/_ref/ (git-ignored).  No-op where /root/reference is
+    absent (the GPU box uses the staged copy that travelled with the snapshot)."""
+    import filecmp
+    import shutil
+    if not os.path.isfile(os.path.join(SRC_DIR, "nerf.py")):
+        return os.path.isfile(os.path.join(STAGE_DIR, "nerf.py"))
+    os.makedirs(STAGE_DIR, exist_ok=True)
+    for name in ("nerf.py", "loader.py"):
+        src, dst = os.path.join(SRC_DIR, name), os.path.join(STAGE_DIR, name)
+        if not (os.path.isfile(dst) and filecmp.cmp(src, dst, shallow=False)):
+            shutil.copyfile(src, dst)
+    return True
 
 
 def import_reference():
