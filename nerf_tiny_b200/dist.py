@@ -128,7 +128,8 @@ def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local
     world = dist.get_world_size(group)
-    per = (n_total + world - 1) // world
+    first = shard_slice(n_total, 0, world)
+    per = first.stop - first.start                     # every shard but the last ones has this many rows
     pad = torch.zeros(per, *local.shape[1:], dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     out = [torch.empty_like(pad) for _ in range(world)]

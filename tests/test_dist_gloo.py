@@ -25,7 +25,7 @@ def _batch(step_zero=False):
     row, col, pix, pb, pic = synth.random_batch(rows17, 10, h, w, torch.Generator().manual_seed(21))
     if step_zero:
         pb = pb.clone()
-        pb[7, 16] = pb[7, 15]                                                  # a degenerate ray in rank 1's shard
+        pb[9, 16] = pb[9, 15]                                                  # a degenerate ray in rank 1's shard (rays 8-9)
     return row, col, pix, pb, synth.k_inv_of(h, w, f)
 
 

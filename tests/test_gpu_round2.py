@@ -214,7 +214,7 @@ def test_sharded_globals_step_zero_branch(dev):
     """A degenerate ray (near == far) in the LAST shard switches numpy's linspace formula for every ray of the batch
     (nerf.py:288): the device-reduced flag and delta0 equal the oracle's global values."""
     D, g, m, row, col, pb, kinv = _shard_setup(dev, "fp32", n=10)
-    pb[7, 16] = pb[7, 15]
+    pb[9, 16] = pb[9, 15]                                     # shards are 4-ray aligned: rays 0-7 | 8-9
     shards = _emulated_shards(D, m, pb, dev, 2)
     pbf = pb.to(dev, torch.float32)
     for r in range(2):
