@@ -135,12 +135,14 @@ int nt_pack_weights(nt_ctx* ctx, int precision, const float* params, void* packe
 int nt_mlp_forward(nt_ctx* ctx, int precision, int64_t n, int p, const float* t, const float* rays,
                    const float* dir_enc, const float* params, const void* packed, float* rgb, float* sigma,
                    void* ws, size_t ws_bytes, int train, void* stream);
-/* autograd of the above (nerf.py:473): g_rgb dev [N,P,3], g_sigma dev [N,P]; grads dev flat
+/* autograd of the above (nerf.py:473): rgb dev [N,P,3] = the colour output of the matching nt_mlp_forward call
+ * (sigmoid' = y(1-y); the caller owns that buffer anyway); g_rgb dev [N,P,3], g_sigma dev [N,P]; grads dev flat
  * (ACCUMULATED into); g_t dev [N,P] or NULL (written, not accumulated; needed for the fine pass
  * only, because t_fine is not detached, nerf.py:255-259). */
 int nt_mlp_backward(nt_ctx* ctx, int precision, int64_t n, int p, const float* t, const float* rays,
-                    const float* dir_enc, const float* params, const void* packed, const float* g_rgb,
-                    const float* g_sigma, float* grads, float* g_t, void* ws, size_t ws_bytes, void* stream);
+                    const float* dir_enc, const float* params, const void* packed, const float* rgb,
+                    const float* g_rgb, const float* g_sigma, float* grads, float* g_t, void* ws, size_t ws_bytes,
+                    void* stream);
 
 /* Diagnostic (NT_PREC_BF16): as nt_mlp_forward, and dumps the fp32 post-activation output of one tensor-core
  * layer (0..7 trunk nerf.py:85-91, 8 point_info :96, 9 dir_info :98) to dbg dev [N*P,256]. */

@@ -52,7 +52,7 @@ SIGNATURES = {
     "nt_packed_weight_bytes": (sz, [vp, i32]),
     "nt_pack_weights": (i32, [vp, i32, vp, vp, vp]),
     "nt_mlp_forward": (i32, [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, i32, vp]),
-    "nt_mlp_backward": (i32, [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "nt_mlp_backward": (i32, [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "nt_mlp_forward_debug": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     "nt_gemm_bf16_debug": (i32, [vp, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp, i32, vp]),
     "nt_composite_coarse": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),

@@ -161,8 +161,9 @@ extern "C" int nt_mlp_forward(nt_ctx* ctx, int precision, int64_t n, int p, cons
 }
 
 extern "C" int nt_mlp_backward(nt_ctx* ctx, int precision, int64_t n, int p, const float* t, const float* rays,
-                               const float* dir_enc, const float* params, const void* packed, const float* g_rgb,
-                               const float* g_sigma, float* grads, float* g_t, void* ws, size_t ws_bytes, void* stream) {
+                               const float* dir_enc, const float* params, const void* packed, const float* rgb,
+                               const float* g_rgb, const float* g_sigma, float* grads, float* g_t, void* ws,
+                               size_t ws_bytes, void* stream) {
   NT_ENTER(ctx);
   (void)dir_enc;
   (void)packed;
@@ -170,7 +171,7 @@ extern "C" int nt_mlp_backward(nt_ctx* ctx, int precision, int64_t n, int p, con
   NT_REQUIRE(precision == NT_PREC_FP32 || precision == NT_PREC_BF16, "unknown precision");
   if (n == 0) return NT_OK;
   if (precision == NT_PREC_BF16)
-    return nt_mlp_bf16_train_backward(ctx, n, p, t, rays, params, nullptr, g_rgb, g_sigma, grads, g_t, ws, ws_bytes,
+    return nt_mlp_bf16_train_backward(ctx, n, p, t, rays, params, rgb, g_rgb, g_sigma, grads, g_t, ws, ws_bytes,
                                       (cudaStream_t)stream);
   return nt_mlp_f32_backward(ctx, n, p, t, rays, params, g_rgb, g_sigma, grads, g_t, ws, ws_bytes, (cudaStream_t)stream);
 }
@@ -283,7 +284,7 @@ extern "C" int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const f
                                     w.g_rgb_c, w.g_sig_c, w.g_rgb_f, w.g_sig_f, w.g_t_f, stream));
   // fine MLP: dW + input gradient down to t_fine (B.4, B.6, B.7)
   const bool detach = ctx->opt_detach_t_fine != 0;
-  NT_TRY(nt_mlp_backward(ctx, precision, n, nf, w.t_f, w.rays, w.dir_enc, params, packed, w.g_rgb_f, w.g_sig_f, grads,
+  NT_TRY(nt_mlp_backward(ctx, precision, n, nf, w.t_f, w.rays, w.dir_enc, params, packed, w.rgb_f, w.g_rgb_f, w.g_sig_f, grads,
                          detach ? nullptr : w.g_t_mlp, w.mlp_f, w.mlp_f_bytes, stream));
   // g_t_fine = compositing path + MLP-input path; then resample backward (B.5)
   if (!detach) {
@@ -298,7 +299,7 @@ extern "C" int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const f
   NT_TRY(nt_launch_axpy(ctx, n * nc * 3, g_rgb_c2, w.g_rgb_c, (cudaStream_t)stream));
   NT_TRY(nt_launch_axpy(ctx, n * nc, g_sig_c2, w.g_sig_c, (cudaStream_t)stream));
   // coarse MLP: dW only (t_coarse is a constant)
-  NT_TRY(nt_mlp_backward(ctx, precision, n, nc, w.t_c, w.rays, w.dir_enc, params, packed, w.g_rgb_c, w.g_sig_c, grads,
+  NT_TRY(nt_mlp_backward(ctx, precision, n, nc, w.t_c, w.rays, w.dir_enc, params, packed, w.rgb_c, w.g_rgb_c, w.g_sig_c, grads,
                          nullptr, w.mlp_c, w.mlp_c_bytes, stream));
   return NT_OK;
 }

@@ -162,6 +162,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
                 }
               }
               if (kc == nch - 1) {
+                // Issuing these stores from an elected epilogue thread instead (so that this thread never waits on the TMA unit)
+                // was measured SLOWER: 428-447 vs 395 us per 1024-ray step - the cost of the stash is contention in the
+                // memory system (342 us with no stores at all), not this wait.
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // epilogue will overwrite the operand tile
                 umma_commit(bar(BAR_ACC_FULL + tl));
               }
@@ -332,7 +335,8 @@ int nt_bwd_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t 
 }
 
 // g_u bf16 [S][128] -> outs[0] = g_info, outs[1..8] = g_7 .. g_0 (bf16 [S][256] each); db[k] accumulates colsum(outs[k])
-int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9], const void* packed, const uint32_t* bits,
+int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9], const int out_ld[9], const void* packed,
+                    const uint32_t* bits,
                     const float* gzsig, const float* wsig, float* const db[9], cudaStream_t st) {
   if (S <= 0) return NT_OK;
   if (!(ctx->attr_done & NT_ATTR_BWD_TC)) {
@@ -344,7 +348,7 @@ int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9]
   int rc = nt_make_map_bf16(&P.map_gu, g_u, S, 128, 128, 64, TILE_M);
   if (rc != NT_OK) return rc;
   for (int i = 0; i < N_STEPS; ++i) {
-    rc = nt_make_map_bf16(&P.map_out[i], outs[i], S, 256, 256, 64, TILE_M);
+    rc = nt_make_map_bf16(&P.map_out[i], outs[i], S, 256, out_ld[i], 64, TILE_M);
     if (rc != NT_OK) return rc;
     P.db[i] = db[i];
   }

@@ -207,5 +207,6 @@ int nt_make_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t c
 // bwd_tc.cu — fused backward-data chain
 size_t nt_bwd_tc_packed_bytes();
 int nt_bwd_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t st);
-int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9], const void* packed, const uint32_t* bits,
+int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9], const int out_ld[9], const void* packed,
+                    const uint32_t* bits,
                     const float* gzsig, const float* wsig, float* const db[9], cudaStream_t st);

@@ -273,8 +273,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
                 mbar_wait(bar(BAR_ACT_READY + tl), lit & 1);
                 tc_fence_after();
                 TC_PROF(tl);
-                if (STASH && P.use_tma_stash && L == 0) {
-                  // layer 0's operand = the xyz features: stash them from smem
+                if (STASH && P.use_tma_stash == 3 && L == 0) {
+                  // (legacy scheme, NT_STASH_MODE=3) layer 0's operand = the xyz features: stash them from smem
                   const int row0 = (pair * 2 + tl) * TILE_M;
                   if (row0 < P.total) {
                     tma_store_2d(&P.st_map[9], 0, row0, sbase + OFF_ENC + tl * CHUNK_A_BYTES);
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 4; ++j)  // 4 x (K = 16) inside the 64-wide swizzled chunk: +32 B per step
                 umma_bf16(d_tmem, umma_desc(a_addr + j * 32), umma_desc(b_addr + j * 32), idesc, (kc | j) != 0);
-              if (STASH && P.use_tma_stash && L > 0) {
+              if (STASH && P.use_tma_stash == 3 && L > 0) {
                 // this K-chunk of the operand = 64 columns of the previous layer's bf16 output (chunk 4 of dir_info = the
                 // view features): stash it from smem.  One 16 KB box per chunk step, not the whole tile at once, so the
                 // weight loads of the next chunks are not queued behind 128 KB of stores in the TMA unit.
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
               }
               if (kc == nch - 1) {
                 // the epilogue that this commit releases overwrites the operand tiles: TMA stash reads must be done
-                if (STASH && P.use_tma_stash) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (STASH && P.use_tma_stash == 3) tma_store_wait_read0();
                 umma_commit(bar(BAR_ACC_FULL + tl));
               }
             }
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
           }
         }
       }
-      if (STASH && P.use_tma_stash) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (STASH && P.use_tma_stash == 3) tma_store_wait0();
     }
   } else {
     // ===================== encode + epilogue warps: per tile 4 lane quadrants x 2 column halves =============
@@ -339,7 +339,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
     uint32_t it = 0;
     int pair_local = 0;
     const int pslot = 4 + 3 * (warp >> 2);  // per warp-group stamp slots (lane 0 of warps 0, 4, 8, 12)
+    // Training stash (use_tma_stash == 1): ONE elected thread per tile writes every operand tile to HBM with TMA tensor
+    // stores right after the tile's 8 epilogue warps have produced it (256-thread named barrier), i.e. while the tensor
+    // core multiplies it, and makes sure the stores have finished READING shared memory before the same warps overwrite
+    // the tile in the next epilogue.  The MMA thread never waits on the TMA unit.
+    const bool tma_stash = STASH && P.use_tma_stash == 1;
+    const bool stasher = tma_stash && (warp & 3) == 0 && half == 0 && lane == 0;
+    const int tile_bar = 9 + tl;
     for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pair_local) {
+      const int row0 = (pair * 2 + tl) * TILE_M;
       const int64_t s = ((int64_t)pair * 2 + tl) * TILE_M + row;
       const bool valid = s < P.total;
       const int64_t sc = valid ? s : P.total - 1;
@@ -379,13 +387,22 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
         }
       }
       fence_proxy_async();
+      if (tma_stash) asm volatile("bar.sync %0, 256;" ::"r"(tile_bar) : "memory");
       tc_fence_before();
       mbar_arrive(bar(BAR_ACT_READY + tl));
+      if (stasher && row0 < P.total) {  // the xyz features of the tile
+        tma_store_2d(&P.st_map[9], 0, row0, enc);
+        tma_store_commit();
+      }
 
       for (int L = 0; L < N_MMA_LAYERS; ++L, ++it) {
         mbar_wait(bar(BAR_ACC_FULL + tl), it & 1);
         tc_fence_after();
         mbar_wait(bar(BAR_AUX_FULL), it & 1);
+        if (tma_stash) {  // the stash stores of this tile's operands have left shared memory: it may be overwritten
+          if (stasher) tma_store_wait_read0();
+          asm volatile("bar.sync %0, 256;" ::"r"(tile_bar) : "memory");
+        }
         if ((warp & 3) == 0 && lane == 0) TC_PROF(pslot);
         if (L == 7)
           epilogue_layer<EPI_RELU_SIGMA, DBG, STASH>(P, L, half, tmem_row, act, aux_s, pair_bar, sw, s, valid);
@@ -425,12 +442,28 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
         if ((warp & 3) == 0 && lane == 0) TC_PROF(pslot + 1);
         if (L != 9) {
           fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          if (tma_stash) asm volatile("bar.sync %0, 256;" ::"r"(tile_bar) : "memory");
           tc_fence_before();
           mbar_arrive(bar(BAR_ACT_READY + tl));
+          if (stasher && row0 < P.total) {
+            // this layer's bf16 output = the operand the tensor core reads next: 4 boxes of 64 columns, at most two in
+            // flight so that the weight ring's loads are never queued behind more than 32 KB of stores in the TMA unit
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              tma_store_2d(&P.st_map[L], c * 64, row0, act + c * CHUNK_A_BYTES);
+              tma_store_commit();
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            }
+            if (L == 4) {  // the view features just written over the xyz features
+              tma_store_2d(&P.st_map[10], 0, row0, enc);
+              tma_store_commit();
+            }
+          }
         }
         if ((warp & 3) == 0 && lane == 0) TC_PROF(pslot + 2);
       }
     }
+    if (stasher) tma_store_wait0();
   }
 
   __syncwarp();
@@ -1065,7 +1098,12 @@ static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const fl
     if (rc != NT_OK) return rc;
     rc = nt_make_map_bf16(&P.st_map[10], stash->denc, S, 64, 64, 64, TILE_M);
     if (rc != NT_OK) return rc;
-    P.use_tma_stash = getenv("NT_NO_TMA_STASH") ? 0 : 1;
+    // NT_STASH_MODE: 3 (default) TMA stash stores issued by the MMA thread, one 16 KB box after each K-chunk's MMAs; 1: issued
+    // by an elected epilogue thread per tile right after the epilogue (measured 8 % slower: 448 vs 415 us per 1024-ray step,
+    // the four boxes arrive at the TMA unit as a burst in front of the weight ring's loads); 0: plain global stores from the
+    // epilogue registers; 2: no stash stores at all (timing experiment only: 322 us)
+    const char* sm = getenv("NT_STASH_MODE");
+    P.use_tma_stash = sm ? atoi(sm) : 3;
     P.st_bits = stash->bits;
   }
   P.t = t;

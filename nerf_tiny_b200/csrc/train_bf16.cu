@@ -16,20 +16,17 @@ typedef __nv_bfloat16 bf16;
 
 struct Ws {
   TcStash st;
-  float* rgb;
   bf16 *GI, *GS[8], *Gu, *Gz, *Gzs, *WT;  // GI = d point_info, GS[i] = d pre-activation of trunk layer i
+  int ldgs[8];                             // row pitch of GS[i]: g_4 and g_0 share one [S][512] buffer (columns 0-255 | 256-511)
   float *gzsig, *genc;
   void* WB;  // transposed weights in the fused backward-data kernel's chunk format
   size_t bytes;
 };
 
-// transposed-weight pack (bf16, each [N][K] K-major for the dX GEMMs)
-constexpr int WT_TRUNK = 0;                       // i = 1..7 : (W_i[:, :256])^T  [256][256] each
-constexpr int WT_INFO = 7 * 65536;                // W_p^T [256][256]
-constexpr int WT_DIRINFO = WT_INFO + 65536;       // (W_d[:, 24:280])^T [256][128]
-constexpr int WT_ENC4 = WT_DIRINFO + 256 * 128;   // (W_4[:, 256:316])^T [64][256] (rows 60..63 zero)
-constexpr int WT_ENC0 = WT_ENC4 + 64 * 256;       // W_0^T [64][256]
-constexpr int WT_ELEMS = WT_ENC0 + 64 * 256;
+// transposed weights of the two layers that read the xyz features, for the ONE GEMM that produces the fp32 gradient
+// w.r.t. those features:  g_enc [S][64] = [g_4 | g_0] [S][512] . WT^T,  WT [64 (feature n, rows 60..63 zero)][512]:
+// k < 256 -> W_4[k][256 + n] (skip connection, nerf.py:109), k >= 256 -> W_0[k - 256][n]
+constexpr int WT_ELEMS = 64 * 512;
 
 Ws carve(void* base, int64_t S) {
   Ws w;
@@ -45,9 +42,12 @@ Ws carve(void* base, int64_t S) {
   w.st.enc = take(S * 64 * 2);
   w.st.denc = take(S * 64 * 2);
   w.st.zsig = (float*)take(S * 4);
-  w.rgb = (float*)take(S * 12);
   w.GI = (bf16*)take(S * 256 * 2);
-  for (int i = 0; i < 8; ++i) w.GS[i] = (bf16*)take(S * 256 * 2);
+  bf16* g40 = (bf16*)take(S * 512 * 2);
+  for (int i = 0; i < 8; ++i) {
+    w.ldgs[i] = (i == 4 || i == 0) ? 512 : 256;
+    w.GS[i] = i == 4 ? g40 : (i == 0 ? g40 + 256 : (bf16*)take(S * 256 * 2));
+  }
   w.Gu = (bf16*)take(S * 128 * 2);
   w.Gz = (bf16*)take(S * 8 * 2);
   w.Gzs = (bf16*)take(S * 8 * 2);
@@ -68,54 +68,56 @@ struct TransposeArgs {
 __global__ void pack_transposed_kernel(const float* __restrict__ params, bf16* __restrict__ wt, TransposeArgs a) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= WT_ELEMS) return;
+  const int n = gid / 512, k = gid % 512;
   float v = 0.f;
-  if (gid < WT_INFO) {  // trunk layers 1..7: out[n = in col][k = out row]
-    const int i = 1 + gid / 65536, r = gid % 65536, nn = r / 256, k = r % 256;
-    v = params[a.w_off[i] + (int64_t)k * a.in_f[i] + nn];
-  } else if (gid < WT_DIRINFO) {
-    const int r = gid - WT_INFO, nn = r / 256, k = r % 256;
-    v = params[a.w_off[L_INFO] + k * 256 + nn];
-  } else if (gid < WT_ENC4) {
-    const int r = gid - WT_DIRINFO, nn = r / 128, k = r % 128;  // n = info column, k = dir_info output
-    v = params[a.w_off[L_DIR] + k * 280 + 24 + nn];
-  } else if (gid < WT_ENC0) {
-    const int r = gid - WT_ENC4, nn = r / 256, k = r % 256;
-    v = nn < 60 ? params[a.w_off[L_P4] + k * 316 + 256 + nn] : 0.f;
-  } else {
-    const int r = gid - WT_ENC0, nn = r / 256, k = r % 256;
-    v = nn < 60 ? params[a.w_off[L_P0] + k * 60 + nn] : 0.f;
-  }
+  if (n < 60) v = k < 256 ? params[a.w_off[L_P4] + k * 316 + 256 + n] : params[a.w_off[L_P0] + (k - 256) * 60 + n];
   wt[gid] = __float2bfloat16_rn(v);
 }
 
-// head activations backward (B.6) + the colour layer's input gradient + the dir_info bias gradient.
-// Phase 1: one thread per sample (sigmoid' / abs', fp32 bias gradients of the two heads by warp reduction).
-// Phase 2: the warp walks its 32 samples together, lane = 4 columns of the 128-wide row, so the u row is read and the
-// g_u row written as one contiguous 256 B access per sample; each lane keeps the fp32 column sums of what it produced
-// (= db of dir_info), reduced over the block's 4 warps in shared memory and added with one atomic per column per block.
-__global__ void __launch_bounds__(128) heads_backward_kernel(int64_t S, const float* __restrict__ rgb,
+// head activations backward (B.6) + the colour layer's input gradient + the dir_info bias gradient, HBM-bound:
+// 256 B (u) read + 256 B (g_u) written per sample plus ~70 B of head values.
+// A block owns HB_ROWS consecutive samples.  Phase 1: one thread per sample evaluates sigmoid' / abs' (fp32), leaves
+// g_z in shared memory and feeds the two head-bias gradients (fp32 block sums: a bf16 column sum would cancel
+// catastrophically on the sigma bias).  Phase 2: thread = (row r of 16, 8-column group cg of 16): 16-byte loads of u,
+// g_u = relu'(u) * (g_z . W_c) (nerf.py:98-99), 16-byte stores; every thread keeps the fp32 column sums of what it
+// produced (= db of dir_info), reduced over the 16 row-threads in shared memory -> one atomic per column per block.
+constexpr int HB_ROWS = 256;
+__global__ void __launch_bounds__(256) heads_backward_kernel(int64_t S, const float* __restrict__ rgb,
                                                              const float* __restrict__ zsig, const float* __restrict__ g_rgb,
                                                              const float* __restrict__ g_sigma, const bf16* __restrict__ U,
                                                              const float* __restrict__ Wc, bf16* __restrict__ Gz,
                                                              bf16* __restrict__ Gzs, float* __restrict__ gzsig,
                                                              bf16* __restrict__ Gu, float* __restrict__ db_col,
                                                              float* __restrict__ db_sig, float* __restrict__ db_dir) {
-  __shared__ float part[4][128];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = s < S;
-  float gz[3] = {0.f, 0.f, 0.f};
-  float gs = 0.f;
-  if (live) {
+  __shared__ float s_gz[HB_ROWS][3];
+  __shared__ float s_part[16][128];
+  __shared__ float s_head[8][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t s0 = (int64_t)blockIdx.x * HB_ROWS;
+  {
+    const int64_t s = s0 + tid;
+    float gz[3] = {0.f, 0.f, 0.f}, gs = 0.f;
+    if (s < S) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float y = rgb[s * 3 + c];
-      gz[c] = g_rgb[s * 3 + c] * y * (1.f - y);
+      for (int c = 0; c < 3; ++c) {
+        const float y = rgb[s * 3 + c];
+        gz[c] = g_rgb[s * 3 + c] * y * (1.f - y);
+      }
+      const float z = zsig[s];
+      gs = z > 0.f ? g_sigma[s] : (z < 0.f ? -g_sigma[s] : 0.f);
+      gzsig[s] = gs;
+      uint4 o;
+      o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[0])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[1])) << 16);
+      o.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[2]));
+      o.z = o.w = 0u;
+      *reinterpret_cast<uint4*>(Gz + s * 8) = o;
+      o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gs));
+      o.y = 0u;
+      *reinterpret_cast<uint4*>(Gzs + s * 8) = o;
     }
-    const float z = zsig[s];
-    gs = z > 0.f ? g_sigma[s] : (z < 0.f ? -g_sigma[s] : 0.f);
-  }
-  {  // bias gradients of the two heads from the fp32 values (the sums cancel heavily: do not round to bf16 first)
+    s_gz[tid][0] = gz[0];
+    s_gz[tid][1] = gz[1];
+    s_gz[tid][2] = gz[2];
     float r0 = gz[0], r1 = gz[1], r2 = gz[2], r3 = gs;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -125,57 +127,63 @@ __global__ void __launch_bounds__(128) heads_backward_kernel(int64_t S, const fl
       r3 += __shfl_xor_sync(0xffffffffu, r3, o);
     }
     if (lane == 0) {
-      atomicAdd(db_col + 0, r0);
-      atomicAdd(db_col + 1, r1);
-      atomicAdd(db_col + 2, r2);
-      atomicAdd(db_sig, r3);
+      s_head[warp][0] = r0;
+      s_head[warp][1] = r1;
+      s_head[warp][2] = r2;
+      s_head[warp][3] = r3;
     }
   }
-  if (live) {
-    gzsig[s] = gs;
-    uint4 o;
-    o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[0])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[1])) << 16);
-    o.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gz[2]));
-    o.z = o.w = 0u;
-    *reinterpret_cast<uint4*>(Gz + s * 8) = o;
-    o.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gs));
-    o.y = 0u;
-    *reinterpret_cast<uint4*>(Gzs + s * 8) = o;
+  __syncthreads();
+  if (tid < 4) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_head[w][tid];
+    atomicAdd(tid < 3 ? db_col + tid : db_sig, t);
   }
-  // g_u = relu'(u) * (g_z . W_c)   (nerf.py:98-99): this lane's 4 columns of the colour weights stay in registers
-  float wc[3][4];
+  const int cg = tid & 15, r = tid >> 4;  // columns cg*8 .. +7, rows r, r+16, ...
+  float wc[3][8];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) wc[c][k] = __ldg(Wc + c * 128 + lane * 4 + k);  // flat parameters are only 4-byte aligned
+    for (int k = 0; k < 8; ++k) wc[c][k] = __ldg(Wc + c * 128 + cg * 8 + k);  // flat parameters are only 4-byte aligned
   }
-  float cs[4] = {0.f, 0.f, 0.f, 0.f};
-  const int64_t s_warp = (int64_t)blockIdx.x * blockDim.x + warp * 32;
+  float cs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cs[k] = 0.f;
 #pragma unroll 4
-  for (int i = 0; i < 32; ++i) {
-    const float z0 = __shfl_sync(0xffffffffu, gz[0], i), z1 = __shfl_sync(0xffffffffu, gz[1], i),
-                z2 = __shfl_sync(0xffffffffu, gz[2], i);
-    const int64_t si = s_warp + i;
-    if (si >= S) break;  // uniform across the warp
-    const uint2 u2 = *reinterpret_cast<const uint2*>(U + si * 128 + lane * 4);
-    const uint32_t uh[4] = {u2.x & 0xffffu, u2.x >> 16, u2.y & 0xffffu, u2.y >> 16};
-    float g[4];
+  for (int i = 0; i < HB_ROWS / 16; ++i) {
+    const int rr = i * 16 + r;
+    const int64_t s = s0 + rr;
+    if (s >= S) break;
+    const uint4 u4 = *reinterpret_cast<const uint4*>(U + s * 128 + cg * 8);
+    const float z0 = s_gz[rr][0], z1 = s_gz[rr][1], z2 = s_gz[rr][2];
+    const uint32_t uw[4] = {u4.x, u4.y, u4.z, u4.w};
+    uint32_t ow[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      g[k] = z0 * wc[0][k] + z1 * wc[1][k] + z2 * wc[2][k];
-      if (!(uh[k] != 0 && uh[k] < 0x8000u)) g[k] = 0.f;  // u > 0 as a bf16 bit pattern
-      cs[k] += g[k];
+    for (int e = 0; e < 4; ++e) {
+      float g[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = 2 * e + h;
+        const uint32_t ub = h ? (uw[e] >> 16) : (uw[e] & 0xffffu);
+        float v = z0 * wc[0][k] + z1 * wc[1][k] + z2 * wc[2][k];
+        if (!(ub != 0 && ub < 0x8000u)) v = 0.f;  // u > 0 as a bf16 bit pattern
+        cs[k] += v;
+        g[h] = v;
+      }
+      ow[e] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g[0])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g[1])) << 16);
     }
-    uint2 o2;
-    o2.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g[0])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g[1])) << 16);
-    o2.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g[2])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(g[3])) << 16);
-    *reinterpret_cast<uint2*>(Gu + si * 128 + lane * 4) = o2;
+    *reinterpret_cast<uint4*>(Gu + s * 128 + cg * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) part[warp][lane * 4 + k] = cs[k];
+  for (int k = 0; k < 8; ++k) s_part[r][cg * 8 + k] = cs[k];
   __syncthreads();
-  const int col = threadIdx.x;
-  atomicAdd(db_dir + col, (part[0][col] + part[1][col]) + (part[2][col] + part[3][col]));
+  if (tid < 128) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) t += s_part[q][tid];
+    atomicAdd(db_dir + tid, t);
+  }
 }
 
 GemmTcEpi epi0() {
@@ -203,15 +211,17 @@ int nt_mlp_bf16_train_forward(nt_ctx* ctx, int64_t n, int p, const float* t, con
     nt_set_error("bf16 train workspace too small: have %zu need %zu", ws_bytes, w.bytes);
     return NT_ERR_WORKSPACE;
   }
-  NT_TRY(nt_mlp_tc_forward_stash(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, &w.st, st));
-  NT_CUDA(cudaMemcpyAsync(w.rgb, rgb, (size_t)S * 12, cudaMemcpyDeviceToDevice, st));
-  return NT_OK;
+  // the colour head's backward needs rgb: the caller keeps the forward's rgb buffer alive and passes it to the backward
+  return nt_mlp_tc_forward_stash(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, &w.st, st);
 }
 
 int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* params,
-                               const float* rgb_unused, const float* g_rgb, const float* g_sigma, float* G, float* g_t,
+                               const float* rgb, const float* g_rgb, const float* g_sigma, float* G, float* g_t,
                                void* ws, size_t ws_bytes, cudaStream_t st) {
-  (void)rgb_unused;
+  if (!rgb) {
+    nt_set_error("bf16 backward needs the forward pass's rgb output");
+    return NT_ERR_INVALID;
+  }
   const int64_t S64 = n * p;
   if (S64 == 0) return NT_OK;
   if (S64 > (int64_t)1 << 30) {
@@ -230,7 +240,7 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
   const bf16* ENC = (const bf16*)w.st.enc;
   const bf16* DENC = (const bf16*)w.st.denc;
 
-  {
+  if (g_t) {
     TransposeArgs a;
     for (int i = 0; i < NT_N_LAYERS; ++i) {
       a.w_off[i] = (int)T.w[i];
@@ -239,7 +249,7 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
     pack_transposed_kernel<<<(WT_ELEMS + 255) / 256, 256, 0, st>>>(P, w.WT, a);
     NT_LAUNCH_CHECK(ctx);
   }
-  heads_backward_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(S, w.rgb, w.st.zsig, g_rgb, g_sigma, H[9],
+  heads_backward_kernel<<<(unsigned)((S + HB_ROWS - 1) / HB_ROWS), 256, 0, st>>>(S, rgb, w.st.zsig, g_rgb, g_sigma, H[9],
                                                                      P + T.w[L_COLOR], w.Gz, w.Gzs, w.gzsig, w.Gu,
                                                                      G + T.b[L_COLOR], G + T.b[L_SIGMA], G + T.b[L_DIR]);
   NT_LAUNCH_CHECK(ctx);
@@ -249,20 +259,6 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
   auto dW = [&](const bf16* Gm, int ldg, int M, const bf16* Hm, int ldh, int N, float* dst, int ldc) {
     return nt_dw_group_add(Gm, ldg, M, Hm, ldh, N, dst, ldc);
   };
-  // dX also accumulates the column sums of what it stores = the bias gradient of the layer that produced `mask`
-  auto dX = [&](const bf16* Gm, int ldg, int K, const bf16* WTm, int N, bf16* out, const bf16* mask, const float* r1_row,
-                const float* r1_col, float* db) {
-    GemmTcEpi e = epi0();
-    e.C = out;
-    e.ldc = N;
-    e.mask = mask;
-    e.ldmask = N;
-    e.r1_row = r1_row;
-    e.r1_col = r1_col;
-    e.colsum = db;
-    return nt_launch_gemm_tc(ctx, 0, S, N, K, Gm, ldg, WTm, K, e, st);
-  };
-
   // colour layer (128 -> 3)
   NT_TRY(dW(w.Gz, 8, 3, H[9], 128, 128, G + T.w[L_COLOR], 128));
   // dir_info on [dir_enc | point_info] (nerf.py:118)
@@ -274,32 +270,25 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
     void* outs[9] = {w.GI, w.GS[7], w.GS[6], w.GS[5], w.GS[4], w.GS[3], w.GS[2], w.GS[1], w.GS[0]};
     float* dbs[9] = {G + T.b[L_INFO], G + T.b[L_P7], G + T.b[L_P6], G + T.b[L_P5], G + T.b[L_P4],
                      G + T.b[L_P3],   G + T.b[L_P2], G + T.b[L_P1], G + T.b[L_P0]};
-    NT_TRY(nt_bwd_tc_chain(ctx, S, w.Gu, outs, w.WB, w.st.bits, w.gzsig, P + T.w[L_SIGMA], dbs, st));
+    const int lds[9] = {256, w.ldgs[7], w.ldgs[6], w.ldgs[5], w.ldgs[4], w.ldgs[3], w.ldgs[2], w.ldgs[1], w.ldgs[0]};
+    NT_TRY(nt_bwd_tc_chain(ctx, S, w.Gu, outs, lds, w.WB, w.st.bits, w.gzsig, P + T.w[L_SIGMA], dbs, st));
   }
   // weight gradients (queued): point_info, sigma head, trunk
   NT_TRY(dW(w.GI, 256, 256, H[7], 256, 256, G + T.w[L_INFO], 256));
   NT_TRY(dW(w.Gzs, 8, 1, H[7], 256, 256, G + T.w[L_SIGMA], 256));
   for (int i = 7; i >= 1; --i) {
-    bf16* cur = w.GS[i];
-    NT_TRY(dW(cur, 256, 256, H[i - 1], 256, 256, G + T.w[i], kLayerIn[i]));
-    if (i == 4) {
-      NT_TRY(dW(cur, 256, 256, ENC, 64, 60, G + T.w[L_P4] + 256, 316));
-      if (g_t) {  // fp32 gradient w.r.t. the xyz features through the skip connection
-        GemmTcEpi e = epi0();
-        e.C = w.genc;
-        e.ldc = 64;
-        e.store_f32 = 1;
-        NT_TRY(nt_launch_gemm_tc(ctx, 0, S, 64, 256, cur, 256, w.WT + WT_ENC4, 256, e, st));
-      }
-    }
+    NT_TRY(dW(w.GS[i], w.ldgs[i], 256, H[i - 1], 256, 256, G + T.w[i], kLayerIn[i]));
+    if (i == 4) NT_TRY(dW(w.GS[4], w.ldgs[4], 256, ENC, 64, 60, G + T.w[L_P4] + 256, 316));
   }
-  NT_TRY(dW(w.GS[0], 256, 256, ENC, 64, 60, G + T.w[L_P0], 60));
+  NT_TRY(dW(w.GS[0], w.ldgs[0], 256, ENC, 64, 60, G + T.w[L_P0], 60));
   if (g_t) {
+    // fp32 gradient w.r.t. the xyz features, skip connection and first layer in ONE GEMM over [g_4 | g_0] (K = 512), then
+    // down to t through the encoder (B.7)
     GemmTcEpi e = epi0();
     e.C = w.genc;
     e.ldc = 64;
-    e.atomic_f32 = 1;  // accumulate onto the skip-connection part
-    NT_TRY(nt_launch_gemm_tc(ctx, 0, S, 64, 256, w.GS[0], 256, w.WT + WT_ENC0, 256, e, st));
+    e.store_f32 = 1;
+    NT_TRY(nt_launch_gemm_tc(ctx, 0, S, 64, 512, w.GS[4], 512, w.WT, 512, e, st));
     NT_TRY(nt_launch_encode_backward(ctx, n, p, t, rays, w.genc, 64, g_t, st));
   }
   NT_TRY(nt_dw_group_flush(ctx, st));

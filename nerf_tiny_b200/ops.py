@@ -100,12 +100,12 @@ class Context:
                                                  _p(sigma), _p(dbg), layer, _st()))
         return rgb, sigma, dbg
 
-    def mlp_backward(self, precision, t, rays, dir_enc, flat, packed, g_rgb, g_sigma, ws, need_gt=True):
+    def mlp_backward(self, precision, t, rays, dir_enc, flat, packed, rgb, g_rgb, g_sigma, ws, need_gt=True):
         n, p = t.shape
         grads = torch.zeros_like(flat)
         g_t = self._f(n, p) if need_gt else None
         _lib.check(self.lib.nt_mlp_backward(self.h, precision, n, p, _p(t), _p(rays), _p(dir_enc), _p(flat), _p(packed),
-                                            _p(g_rgb), _p(g_sigma), _p(grads), _p(g_t), _p(ws), ws.numel(), _st()))
+                                            _p(rgb), _p(g_rgb), _p(g_sigma), _p(grads), _p(g_t), _p(ws), ws.numel(), _st()))
         return grads, g_t
 
     # ---- compositing / resampling ---------------------------------------------------------------------

@@ -250,7 +250,7 @@ def test_mlp_fp32_backward(ctx, dev, golden_dir):
     gen = torch.Generator().manual_seed(4)
     g_rgb = torch.randn(rgb.shape, generator=gen)
     g_sig = torch.randn(sigma.shape, generator=gen) * 0.01
-    grads, g_t = ctx.mlp_backward(FP32, t, rays, de, flat, None, g_rgb.to(dev), g_sig.to(dev), ws)
+    grads, g_t = ctx.mlp_backward(FP32, t, rays, de, flat, None, rgb, g_rgb.to(dev), g_sig.to(dev), ws)
     # fp64 oracle autograd on identical inputs
     sd = {k: v.double().requires_grad_(True) for k, v in sd32.items()}
     tt = torch.from_numpy(g["t_fine"]).double().requires_grad_(True)
@@ -435,7 +435,7 @@ def test_mlp_bf16_backward(ctx, dev, golden_dir, case, tk, wcase):
     gen = torch.Generator().manual_seed(4)
     g_rgb = torch.randn(rgb.shape, generator=gen)
     g_sig = torch.randn(sigma.shape, generator=gen) * 0.01
-    grads, g_t = ctx.mlp_backward(BF16, t, rays, de, flat, packed, g_rgb.to(dev), g_sig.to(dev), ws)
+    grads, g_t = ctx.mlp_backward(BF16, t, rays, de, flat, packed, rgb, g_rgb.to(dev), g_sig.to(dev), ws)
     gflat = grads.cpu().numpy()
     d_cam, d_wrd = O.ray_dirs(g["row"], g["col"], g["k_inv"], g["c2w"])
     out = {}
