@@ -8,7 +8,6 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
-static int nt_launch_axpy(nt_ctx* ctx, int64_t n, const float* x, float* y, cudaStream_t st);
 
 void nt_set_error(const char* fmt, ...) {
   va_list ap;
@@ -35,7 +34,11 @@ extern "C" int nt_layer_table(nt_layer_desc out[NT_N_LAYERS]) {
 
 extern "C" int nt_create(nt_ctx** out, int device, int n_coarse, int n_fine) {
   NT_REQUIRE(out, "null out");
-  NT_REQUIRE(n_coarse == 64 && n_fine == 128, "this build supports n_coarse=64, n_fine=128 (conf/lego.ini, conf/fern.ini)");
+  // nerf.py:170 takes any counts (main.py:28-29 reads N_COARSE / N_FINE from the .ini); the one-warp-per-ray kernels hold
+  // 32-sample slices per lane and the merged ray must fit their 256 sort slots
+  NT_REQUIRE(n_coarse >= 32 && n_coarse <= 128 && n_coarse % 32 == 0 && n_fine >= 32 && n_fine % 32 == 0 &&
+                 n_coarse + n_fine <= 256,
+             "n_coarse / n_fine must be multiples of 32 with n_coarse <= 128 and n_coarse + n_fine <= 256");
   int count = 0;
   NT_CUDA(cudaGetDeviceCount(&count));
   if (device < 0 || device >= count) {
@@ -286,32 +289,15 @@ extern "C" int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const f
   const bool detach = ctx->opt_detach_t_fine != 0;
   NT_TRY(nt_mlp_backward(ctx, precision, n, nf, w.t_f, w.rays, w.dir_enc, params, packed, w.rgb_f, w.g_rgb_f, w.g_sig_f, grads,
                          detach ? nullptr : w.g_t_mlp, w.mlp_f, w.mlp_f_bytes, stream));
-  // g_t_fine = compositing path + MLP-input path; then resample backward (B.5)
-  if (!detach) {
-    NT_TRY(nt_launch_axpy(ctx, n * nf, w.g_t_mlp, w.g_t_f, (cudaStream_t)stream));
-    NT_TRY(nt_sample_pdf_backward(ctx, n, w.t_c, w.w_c, delta0, w.g_t_f, w.g_w_c, stream));
-  }
-  // C_coarse <- composite; rgb/sigma of the coarse samples also feed the fine composite: add both
-  float* g_rgb_c2 = w.g_rgb_f;  // fine-pass buffers are free again: reuse as scratch for the coarse composite grads
-  float* g_sig_c2 = w.g_sig_f;
-  NT_TRY(nt_composite_coarse_backward(ctx, n, near_, far_, w.rgb_c, w.sig_c, g_c_coarse, detach ? nullptr : w.g_w_c,
-                                      g_rgb_c2, g_sig_c2, stream));
-  NT_TRY(nt_launch_axpy(ctx, n * nc * 3, g_rgb_c2, w.g_rgb_c, (cudaStream_t)stream));
-  NT_TRY(nt_launch_axpy(ctx, n * nc, g_sig_c2, w.g_sig_c, (cudaStream_t)stream));
+  // g_t_fine = compositing path + MLP-input path (summed inside the kernel); then resample backward (B.5)
+  if (!detach)
+    NT_TRY(nt_launch_sample_pdf_backward(ctx, n, w.t_c, w.w_c, delta0, w.g_t_f, w.g_t_mlp, w.g_w_c, (cudaStream_t)stream));
+  // C_coarse <- composite; rgb/sigma of the coarse samples also feed the fine composite: accumulate onto those gradients
+  NT_TRY(nt_launch_composite_coarse_backward(ctx, n, near_, far_, w.rgb_c, w.sig_c, g_c_coarse, detach ? nullptr : w.g_w_c,
+                                             w.g_rgb_c, w.g_sig_c, 1, (cudaStream_t)stream));
   // coarse MLP: dW only (t_coarse is a constant)
   NT_TRY(nt_mlp_backward(ctx, precision, n, nc, w.t_c, w.rays, w.dir_enc, params, packed, w.rgb_c, w.g_rgb_c, w.g_sig_c, grads,
                          nullptr, w.mlp_c, w.mlp_c_bytes, stream));
-  return NT_OK;
-}
-
-__global__ void axpy_kernel(int64_t n, const float* __restrict__ x, float* __restrict__ y) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] += x[i];
-}
-static int nt_launch_axpy(nt_ctx* ctx, int64_t n, const float* x, float* y, cudaStream_t st) {
-  if (n <= 0) return NT_OK;
-  axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, x, y);
-  NT_LAUNCH_CHECK(ctx);
   return NT_OK;
 }
 

@@ -9,8 +9,8 @@
 #include "../../include/nerftiny.h"
 
 #define NT_WARP 32
-#define NT_MAX_COARSE 64
-#define NT_MAX_FINE 128
+#define NT_MAX_COARSE 128
+#define NT_MAX_MERGED 256
 #define NT_MAX_DEVICES 64
 
 struct nt_ctx {
@@ -156,6 +156,13 @@ int nt_mlp_tc_forward_dbg(nt_ctx* ctx, int64_t n, int p, const float* t, const f
 size_t nt_mlp_tc32_packed_bytes();
 int nt_mlp_tc32_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                         const void* packed, float* rgb, float* sigma, cudaStream_t st);
+// composite.cu / sample_pdf.cu: backward launchers with the fusions nt_render_backward uses (accumulate onto an existing
+// gradient; second gradient path into t_fine summed on the fly)
+int nt_launch_composite_coarse_backward(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, const float* rgb,
+                                        const float* sigma, const float* g_c, const float* g_w_ext, float* g_rgb,
+                                        float* g_sigma, int accumulate, cudaStream_t st);
+int nt_launch_sample_pdf_backward(nt_ctx* ctx, int64_t n, const float* t_coarse, const float* w, const float* delta0,
+                                  const float* g_t_fine, const float* g_t_fine2, float* g_w, cudaStream_t st);
 // composite_fine_fwd.cu
 int nt_launch_composite_fine_fwd(nt_ctx* ctx, int64_t n, const float* t_c, const float* rgb_c, const float* sigma_c,
                                  const float* t_f, const float* rgb_f, const float* sigma_f, float last, float* c_out,

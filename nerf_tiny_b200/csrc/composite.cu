@@ -140,7 +140,7 @@ template <int EPL>
 __global__ void composite_coarse_bwd_kernel(int64_t n, const float* __restrict__ near_, const float* __restrict__ far_,
                                             const float* __restrict__ rgb, const float* __restrict__ sigma,
                                             const float* __restrict__ g_c, const float* __restrict__ g_w_ext,
-                                            float* __restrict__ g_rgb, float* __restrict__ g_sigma) {
+                                            float* __restrict__ g_rgb, float* __restrict__ g_sigma, int accumulate) {
   constexpr int P = EPL * 32;
   int lane = threadIdx.x & 31;
   int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -157,9 +157,15 @@ __global__ void composite_coarse_bwd_kernel(int64_t n, const float* __restrict__
     int64_t e = ray * P + lane * EPL + k;
     const float* c = rgb + e * 3;
     gw[k] = c[0] * g0 + c[1] * g1 + c[2] * g2 + (g_w_ext ? g_w_ext[e] : 0.f);
-    g_rgb[e * 3 + 0] = w[k] * g0;
-    g_rgb[e * 3 + 1] = w[k] * g1;
-    g_rgb[e * 3 + 2] = w[k] * g2;
+    if (accumulate) {  // the coarse samples also received a gradient from the fine compositing: add to it
+      g_rgb[e * 3 + 0] += w[k] * g0;
+      g_rgb[e * 3 + 1] += w[k] * g1;
+      g_rgb[e * 3 + 2] += w[k] * g2;
+    } else {
+      g_rgb[e * 3 + 0] = w[k] * g0;
+      g_rgb[e * 3 + 1] = w[k] * g1;
+      g_rgb[e * 3 + 2] = w[k] * g2;
+    }
     lsum += gw[k] * w[k];
   }
   // suffix sums of g_w*w: lanes after this one, then within the lane from the back
@@ -169,7 +175,10 @@ __global__ void composite_coarse_bwd_kernel(int64_t n, const float* __restrict__
   for (int k = EPL - 1; k >= 0; --k) {
     run += gw[k] * w[k];
     float ga = te[k] * gw[k] - run;  // B.2
-    g_sigma[ray * P + lane * EPL + k] = ga * delta;
+    if (accumulate)
+      g_sigma[ray * P + lane * EPL + k] += ga * delta;
+    else
+      g_sigma[ray * P + lane * EPL + k] = ga * delta;
   }
 }
 
@@ -230,7 +239,7 @@ __device__ __forceinline__ void load_channel(int ch, int nc, int nf, int64_t ray
   __syncwarp();
 }
 
-template <bool BWD>
+template <bool BWD, int EPL>   // EPL = (nc + nf) / 32
 __global__ void __launch_bounds__(FINE_WARPS * 32)
     composite_fine_kernel(int64_t n, int nc, int nf, const float* __restrict__ t_c, const float* __restrict__ rgb_c,
                           const float* __restrict__ sigma_c, const float* __restrict__ t_f,
@@ -240,13 +249,12 @@ __global__ void __launch_bounds__(FINE_WARPS * 32)
                           const uint8_t* __restrict__ perm_in, const float* __restrict__ g_c, float* __restrict__ g_rgb_c,
                           float* __restrict__ g_sigma_c, float* __restrict__ g_rgb_f, float* __restrict__ g_sigma_f,
                           float* __restrict__ g_t_f) {
-  constexpr int EPL = 6;  // 192 / 32
   __shared__ float s_key[FINE_WARPS][5][FINE_PAD];
   __shared__ uint8_t s_idx[FINE_WARPS][5][FINE_PAD];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ray = (int64_t)blockIdx.x * FINE_WARPS + wib;
   if (ray >= n) return;
-  const int tot = nc + nf;  // 192
+  const int tot = nc + nf;
   float(*key)[FINE_PAD] = s_key[wib];
   uint8_t(*idx)[FINE_PAD] = s_idx[wib];
 
@@ -381,18 +389,6 @@ __global__ void ray_loss_kernel(int64_t n3, const float* __restrict__ cc, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-extern "C" int nt_composite_coarse(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, const float* rgb,
-                                   const float* sigma, float* weights, float* c_out, void* stream) {
-  NT_ENTER(ctx);
-  NT_REQUIRE(ctx && near_ && far_ && rgb && sigma && weights && c_out, "null pointer");
-  NT_REQUIRE(ctx->n_coarse == 64, "coarse compositing is built for Nc=64");
-  if (n <= 0) return NT_OK;
-  composite_coarse_kernel<2><<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(n, near_, far_, rgb, sigma,
-                                                                                       weights, c_out);
-  NT_LAUNCH_CHECK(ctx);
-  return NT_OK;
-}
-
 #define NT_DISPATCH_EPL(P, CALL)                                                     \
   switch ((P) / 32) {                                                               \
     case 1: { constexpr int E = 1; CALL; } break;                                   \
@@ -404,6 +400,18 @@ extern "C" int nt_composite_coarse(nt_ctx* ctx, int64_t n, const float* near_, c
     case 7: { constexpr int E = 7; CALL; } break;                                   \
     default: { constexpr int E = 8; CALL; } break;                                  \
   }
+
+extern "C" int nt_composite_coarse(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, const float* rgb,
+                                   const float* sigma, float* weights, float* c_out, void* stream) {
+  NT_ENTER(ctx);
+  NT_REQUIRE(ctx && near_ && far_ && rgb && sigma && weights && c_out, "null pointer");
+  if (n <= 0) return NT_OK;
+  const unsigned blocks = (unsigned)((n + 3) / 4);
+  NT_DISPATCH_EPL(ctx->n_coarse, (composite_coarse_kernel<E><<<blocks, 128, 0, (cudaStream_t)stream>>>(n, near_, far_, rgb, sigma,
+                                                                                                     weights, c_out)));
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
 
 extern "C" int nt_get_density(nt_ctx* ctx, int64_t n, int p, const float* delta, const float* sigma, float* weights,
                               void* stream) {
@@ -431,17 +439,24 @@ extern "C" int nt_color_cum(nt_ctx* ctx, int64_t n, int p, const float* weights,
   return NT_OK;
 }
 
+int nt_launch_composite_coarse_backward(nt_ctx* ctx, int64_t n, const float* near_, const float* far_, const float* rgb,
+                                        const float* sigma, const float* g_c, const float* g_w_ext, float* g_rgb,
+                                        float* g_sigma, int accumulate, cudaStream_t st) {
+  if (n <= 0) return NT_OK;
+  const unsigned blocks = (unsigned)((n + 3) / 4);
+  NT_DISPATCH_EPL(ctx->n_coarse, (composite_coarse_bwd_kernel<E><<<blocks, 128, 0, st>>>(n, near_, far_, rgb, sigma, g_c, g_w_ext,
+                                                                                       g_rgb, g_sigma, accumulate)));
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
+}
+
 extern "C" int nt_composite_coarse_backward(nt_ctx* ctx, int64_t n, const float* near_, const float* far_,
                                             const float* rgb, const float* sigma, const float* g_c,
                                             const float* g_w_ext, float* g_rgb, float* g_sigma, void* stream) {
   NT_ENTER(ctx);
   NT_REQUIRE(ctx && near_ && far_ && rgb && sigma && g_c && g_rgb && g_sigma, "null pointer");
-  NT_REQUIRE(ctx->n_coarse == 64, "coarse compositing is built for Nc=64");
-  if (n <= 0) return NT_OK;
-  composite_coarse_bwd_kernel<2><<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
-      n, near_, far_, rgb, sigma, g_c, g_w_ext, g_rgb, g_sigma);
-  NT_LAUNCH_CHECK(ctx);
-  return NT_OK;
+  return nt_launch_composite_coarse_backward(ctx, n, near_, far_, rgb, sigma, g_c, g_w_ext, g_rgb, g_sigma, 0,
+                                             (cudaStream_t)stream);
 }
 
 extern "C" int nt_composite_fine(nt_ctx* ctx, int64_t n, const float* t_c, const float* rgb_c, const float* sigma_c,
@@ -449,9 +464,7 @@ extern "C" int nt_composite_fine(nt_ctx* ctx, int64_t n, const float* t_c, const
                                  float* weights, uint8_t* perm, void* stream) {
   NT_ENTER(ctx);
   NT_REQUIRE(ctx && t_c && rgb_c && sigma_c && t_f && rgb_f && sigma_f && c_out, "null pointer");
-  NT_REQUIRE(ctx->n_coarse + ctx->n_fine == 192, "fine compositing is built for Nc+Nf=192");
   if (n <= 0) return NT_OK;
-  NT_REQUIRE(ctx->n_coarse == 64 && ctx->n_fine == 128, "fine compositing is built for Nc=64, Nf=128");
   // forward: the five channel sorts run in registers (composite_fine_fwd.cu); the shared-memory kernel above is
   // kept for the backward pass, which re-gathers through the stored permutations
   return nt_launch_composite_fine_fwd(ctx, n, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, last, c_out, weights, perm,
@@ -466,12 +479,12 @@ extern "C" int nt_composite_fine_backward(nt_ctx* ctx, int64_t n, const float* t
   NT_ENTER(ctx);
   NT_REQUIRE(ctx && t_c && rgb_c && sigma_c && t_f && rgb_f && sigma_f && perm && g_c, "null pointer");
   NT_REQUIRE(g_rgb_c && g_sigma_c && g_rgb_f && g_sigma_f && g_t_f, "null output pointer");
-  NT_REQUIRE(ctx->n_coarse + ctx->n_fine == 192, "fine compositing is built for Nc+Nf=192");
   if (n <= 0) return NT_OK;
-  composite_fine_kernel<true><<<(unsigned)((n + FINE_WARPS - 1) / FINE_WARPS), FINE_WARPS * 32, 0,
-                                (cudaStream_t)stream>>>(n, ctx->n_coarse, ctx->n_fine, t_c, rgb_c, sigma_c, t_f, rgb_f,
-                                                        sigma_f, last, nullptr, nullptr, nullptr, perm, g_c, g_rgb_c,
-                                                        g_sigma_c, g_rgb_f, g_sigma_f, g_t_f);
+  const unsigned blocks = (unsigned)((n + FINE_WARPS - 1) / FINE_WARPS);
+  NT_DISPATCH_EPL(ctx->n_coarse + ctx->n_fine,
+                  (composite_fine_kernel<true, E><<<blocks, FINE_WARPS * 32, 0, (cudaStream_t)stream>>>(
+                      n, ctx->n_coarse, ctx->n_fine, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, last, nullptr, nullptr, nullptr,
+                      perm, g_c, g_rgb_c, g_sigma_c, g_rgb_f, g_sigma_f, g_t_f)));
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;
 }

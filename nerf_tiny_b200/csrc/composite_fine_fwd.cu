@@ -1,5 +1,5 @@
 // Forward of the fine compositing (render_rays nerf.py:302-321) with the five independent channel sorts done in
-// REGISTERS: one warp per ray, the 192 merged samples padded to 256 = 32 lanes x 8 elements, a bitonic network
+// REGISTERS: one warp per ray, the nc + nf (192 by default, at most 256) merged samples padded to 256 = 32 lanes x 8 elements, a bitonic network
 // whose strides >= 8 are warp shuffles and whose strides < 8 stay inside the lane.  Replaces the shared-memory
 // version for the forward pass (the backward re-gathers through the stored permutations and needs no sort).
 // Sorting (key, original index) pairs reproduces a stable sort (ATen CPU) and yields the permutations kept for
@@ -103,21 +103,22 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// loads this lane's 8 merged elements (coarse samples 0..63 | fine 64..191 | +inf padding) of every channel
-__device__ __forceinline__ void load_lane(int64_t ray, int lane, const float* __restrict__ t_c, const float* __restrict__ rgb_c,
+// loads this lane's 8 merged elements (coarse samples 0..nc-1 | fine nc..nc+nf-1 | +inf padding) of every channel;
+// nc and nf are multiples of 32, so a lane's 8 elements never straddle the coarse / fine boundary
+__device__ __forceinline__ void load_lane(int64_t ray, int lane, int nc, int nf, const float* __restrict__ t_c, const float* __restrict__ rgb_c,
                                           const float* __restrict__ sigma_c, const float* __restrict__ t_f,
                                           const float* __restrict__ rgb_f, const float* __restrict__ sigma_f,
                                           float (&ch)[5][8]) {
   const float inf = __int_as_float(0x7f800000);
-  if (lane >= 24) {
+  if (lane * 8 >= nc + nf) {
 #pragma unroll
     for (int c = 0; c < 5; ++c)
 #pragma unroll
       for (int r = 0; r < 8; ++r) ch[c][r] = inf;
     return;
   }
-  const bool co = lane < 8;
-  const int64_t s0 = co ? ray * 64 + lane * 8 : ray * 128 + (lane - 8) * 8;  // first sample of this lane
+  const bool co = lane * 8 < nc;
+  const int64_t s0 = co ? ray * nc + lane * 8 : ray * nf + (lane * 8 - nc);  // first sample of this lane
   const float4* pt = reinterpret_cast<const float4*>((co ? t_c : t_f) + s0);
   const float4* ps = reinterpret_cast<const float4*>((co ? sigma_c : sigma_f) + s0);
   const float4* pc = reinterpret_cast<const float4*>((co ? rgb_c : rgb_f) + s0 * 3);
@@ -141,7 +142,7 @@ __device__ __forceinline__ void load_lane(int64_t ray, int lane, const float* __
 }
 
 template <bool PERM>
-__global__ void __launch_bounds__(128) composite_fine_fwd_kernel(int64_t n, const float* __restrict__ t_c,
+__global__ void __launch_bounds__(128) composite_fine_fwd_kernel(int64_t n, int nc, int nf, const float* __restrict__ t_c,
                                                                  const float* __restrict__ rgb_c,
                                                                  const float* __restrict__ sigma_c,
                                                                  const float* __restrict__ t_f,
@@ -152,8 +153,10 @@ __global__ void __launch_bounds__(128) composite_fine_fwd_kernel(int64_t n, cons
   const int lane = threadIdx.x & 31;
   const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (ray >= n) return;
+  const int tot = nc + nf;
+  const bool live = lane * 8 < tot;
   float ch[5][8];
-  load_lane(ray, lane, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, ch);
+  load_lane(ray, lane, nc, nf, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, ch);
   if (PERM) {
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(128) composite_fine_fwd_kernel(int64_t n, cons
         const uint32_t id = (uint32_t)kv[r] & 0xffu;
         if (r < 4) lo |= id << (8 * r); else hi |= id << (8 * (r - 4));
       }
-      if (lane < 24) *reinterpret_cast<uint2*>(perm + (ray * 5 + c) * 192 + lane * 8) = make_uint2(lo, hi);
+      if (live) *reinterpret_cast<uint2*>(perm + (ray * 5 + c) * tot + lane * 8) = make_uint2(lo, hi);
     }
   } else {
 #pragma unroll
@@ -182,8 +185,8 @@ __global__ void __launch_bounds__(128) composite_fine_fwd_kernel(int64_t n, cons
   for (int r = 0; r < 8; ++r) {
     const int e = lane * 8 + r;
     const float tn = r < 7 ? ch[0][r + 1] : t_next_lane;
-    dl[r] = e < 191 ? __fsub_rn(tn, ch[0][r]) : last;
-    a[r] = e < 192 ? __fmul_rn(dl[r], ch[4][r]) : 0.f;
+    dl[r] = e < tot - 1 ? __fsub_rn(tn, ch[0][r]) : last;
+    a[r] = e < tot ? __fmul_rn(dl[r], ch[4][r]) : 0.f;
     run += (double)a[r];
     pre[r] = run;
   }
@@ -192,15 +195,15 @@ __global__ void __launch_bounds__(128) composite_fine_fwd_kernel(int64_t n, cons
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const float S = (float)(base + pre[r]);
-    w[r] = lane < 24 ? expf(-S) * (1.f - expf(-a[r])) : 0.f;
-    if (lane < 24) {
+    w[r] = live ? expf(-S) * (1.f - expf(-a[r])) : 0.f;
+    if (live) {
       c0 += w[r] * ch[1][r];
       c1 += w[r] * ch[2][r];
       c2 += w[r] * ch[3][r];
     }
   }
-  if (weights && lane < 24) {
-    float4* pw = reinterpret_cast<float4*>(weights + ray * 192 + lane * 8);
+  if (weights && live) {
+    float4* pw = reinterpret_cast<float4*>(weights + ray * tot + lane * 8);
     pw[0] = make_float4(w[0], w[1], w[2], w[3]);
     pw[1] = make_float4(w[4], w[5], w[6], w[7]);
   }
@@ -221,10 +224,10 @@ int nt_launch_composite_fine_fwd(nt_ctx* ctx, int64_t n, const float* t_c, const
                                  float* weights, uint8_t* perm, cudaStream_t st) {
   const unsigned blocks = (unsigned)((n + 3) / 4);
   if (perm)
-    composite_fine_fwd_kernel<true><<<blocks, 128, 0, st>>>(n, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, last, c_out,
+    composite_fine_fwd_kernel<true><<<blocks, 128, 0, st>>>(n, ctx->n_coarse, ctx->n_fine, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, last, c_out,
                                                             weights, perm);
   else
-    composite_fine_fwd_kernel<false><<<blocks, 128, 0, st>>>(n, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, last, c_out,
+    composite_fine_fwd_kernel<false><<<blocks, 128, 0, st>>>(n, ctx->n_coarse, ctx->n_fine, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, last, c_out,
                                                              weights, perm);
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;

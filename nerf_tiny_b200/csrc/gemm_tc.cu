@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };  // full[3] 0-2, empty[3] 3-5, acc_full 6
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
-  const int kb_total = g.S / BK;
+  const int kb_total = (g.S + BK - 1) / BK;  // rows past S are zero-filled by TMA: a partial last block adds nothing
   const int kb0 = blockIdx.x * g.kb_per_cta;
   const int kb1 = min(kb_total, kb0 + g.kb_per_cta);
 
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dw_grouped_kernel(const __gri
   int pr = 0;
   while (pr + 1 < g.n_problems && (int)blockIdx.x >= g.cta_begin[pr + 1]) ++pr;
   const int slot = blockIdx.x - g.cta_begin[pr];
-  const int kb_total = g.S / BK;
+  const int kb_total = (g.S + BK - 1) / BK;  // rows past S are zero-filled by TMA: a partial last block adds nothing
   const int kb0 = slot * g.kb_per_cta[pr];
   const int kb1 = min(kb_total, kb0 + g.kb_per_cta[pr]);
   const int m_valid = g.m_valid[pr], n_valid = g.n_valid[pr];
@@ -739,8 +739,8 @@ struct DwQueue {
 static thread_local DwQueue g_dwq;
 
 int nt_dw_group_begin(int S) {
-  if (S <= 0 || S % BK != 0) {
-    nt_set_error("dw_group: S must be a positive multiple of 64");
+  if (S <= 0) {
+    nt_set_error("dw_group: S must be positive");
     return NT_ERR_INVALID;
   }
   g_dwq.g.n_problems = 0;
@@ -770,7 +770,7 @@ int nt_dw_group_add(const void* G, int ldg, int m_valid, const void* H, int ldh,
 int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st) {
   DwGroup& g = g_dwq.g;
   if (g.n_problems == 0) return NT_OK;
-  const int kb_total = g.S / BK;
+  const int kb_total = (g.S + BK - 1) / BK;  // rows past S are zero-filled by TMA: a partial last block adds nothing
   int wsum = 0;
   for (int i = 0; i < g.n_problems; ++i) wsum += g_dwq.weight[i];
   const int budget = 2 * ctx->sm_count;  // two CTAs' worth of work per SM keeps the tail short

@@ -13,8 +13,6 @@
 
 #define FULL 0xffffffffu
 #define PDF_WARPS 4
-#define NC 64
-#define NF 128
 
 __device__ __forceinline__ double warp_incl_scan_d(double v, int lane) {
 #pragma unroll
@@ -25,19 +23,29 @@ __device__ __forceinline__ double warp_incl_scan_d(double v, int lane) {
   return v;
 }
 
-// builds cdf (smem), returns lo/hi/step; every lane gets the same values
-__device__ __forceinline__ void build_cdf(const float* __restrict__ w_row, float* cdf, float* wsm, int lane, float& lo,
+// builds cdf (smem), returns lo/hi/step; every lane gets the same values.  NC = 32 * EC coarse samples, lane owns
+// elements lane*EC .. lane*EC + EC-1.
+template <int EC>
+__device__ __forceinline__ void build_cdf(const float* __restrict__ w_row, float* cdf, float* wsm, int lane, int nf, float& lo,
                                           float& hi, float& step) {
-  float w0 = w_row[lane * 2], w1 = w_row[lane * 2 + 1];
-  wsm[lane * 2] = w0;
-  wsm[lane * 2 + 1] = w1;
-  double s0 = (double)w0, s1 = s0 + (double)w1;
-  double incl = warp_incl_scan_d(s1, lane);
-  double base = incl - s1;
-  float c0 = (float)(base + s0), c1 = (float)(base + s1);
-  cdf[lane * 2] = c0;
-  cdf[lane * 2 + 1] = c1;
-  float mx = fmaxf(c0, c1), mn = fminf(c0, c1);
+  float wv[EC];
+  double pre[EC], run = 0.0;
+#pragma unroll
+  for (int k = 0; k < EC; ++k) {
+    wv[k] = w_row[lane * EC + k];
+    wsm[lane * EC + k] = wv[k];
+    run += (double)wv[k];
+    pre[k] = run;
+  }
+  const double base = warp_incl_scan_d(run, lane) - run;
+  float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+  for (int k = 0; k < EC; ++k) {
+    const float c = (float)(base + pre[k]);  // every prefix rounded to fp32, like CPU cumsum
+    cdf[lane * EC + k] = c;
+    mx = fmaxf(mx, c);
+    mn = fminf(mn, c);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
@@ -45,16 +53,17 @@ __device__ __forceinline__ void build_cdf(const float* __restrict__ w_row, float
   }
   lo = mn;
   hi = mx;
-  step = __fdiv_rn(__fsub_rn(hi, lo), (float)(NF + 1));
+  step = __fdiv_rn(__fsub_rn(hi, lo), (float)(nf + 1));
   __syncwarp();
 }
 
+template <int NC>
 __device__ __forceinline__ int count_less(const float* cdf, float u) {
   // number of cdf entries strictly below u; cdf is non-decreasing (w >= 0)
   int lo = 0, hi = NC;
 #pragma unroll
-  for (int it = 0; it < 7; ++it) {
-    if (lo < hi) {
+  for (int it = 0; it < 8; ++it) {
+    if ((1 << it) <= NC && lo < hi) {
       int mid = (lo + hi) >> 1;
       if (cdf[mid] < u)
         lo = mid + 1;
@@ -65,10 +74,12 @@ __device__ __forceinline__ int count_less(const float* cdf, float u) {
   return lo;
 }
 
+template <int EC>
 __global__ void __launch_bounds__(PDF_WARPS * 32)
-    sample_pdf_kernel(int64_t n, const float* __restrict__ t_coarse, const float* __restrict__ w,
+    sample_pdf_kernel(int64_t n, int nf, const float* __restrict__ t_coarse, const float* __restrict__ w,
                       const float* __restrict__ delta0_ptr, float* __restrict__ t_fine, int32_t* __restrict__ idx_out,
                       int* __restrict__ status) {
+  constexpr int NC = 32 * EC;
   __shared__ float s_cdf[PDF_WARPS][NC], s_w[PDF_WARPS][NC], s_t[PDF_WARPS][NC];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ray = (int64_t)blockIdx.x * PDF_WARPS + wib;
@@ -76,32 +87,34 @@ __global__ void __launch_bounds__(PDF_WARPS * 32)
   float* cdf = s_cdf[wib];
   float* wsm = s_w[wib];
   float* tc = s_t[wib];
-  tc[lane * 2] = t_coarse[ray * NC + lane * 2];
-  tc[lane * 2 + 1] = t_coarse[ray * NC + lane * 2 + 1];
+#pragma unroll
+  for (int k = 0; k < EC; ++k) tc[lane * EC + k] = t_coarse[ray * NC + lane * EC + k];
   float lo, hi, step;
-  build_cdf(w + ray * NC, cdf, wsm, lane, lo, hi, step);
+  build_cdf<EC>(w + ray * NC, cdf, wsm, lane, nf, lo, hi, step);
   const float delta0 = delta0_ptr ? *delta0_ptr : __fsub_rn(t_coarse[1], t_coarse[0]);  // ray 0 only (nerf.py:234)
   bool bad = false;
-#pragma unroll
-  for (int q = 0; q < NF / 32; ++q) {
+  for (int q = 0; q < nf / 32; ++q) {
     int k = q * 32 + lane;  // output slot, u index k+1
     float u = __fadd_rn(__fmul_rn((float)(k + 1), step), lo);
-    int j = count_less(cdf, u) - 1;
-    if (idx_out) idx_out[ray * NF + k] = j;
-    if (j < 0 || j > NF - 1) bad = true;
+    int j = count_less<NC>(cdf, u) - 1;
+    if (idx_out) idx_out[ray * nf + k] = j;
+    if (j < 0 || j > nf - 1) bad = true;  // nerf.py:251 compares against num_fine - 1
     int jc = min(max(j, 0), NC - 1);
     float slope = (jc < NC - 1) ? __fdiv_rn(delta0, __fadd_rn(wsm[jc + 1], 1e-7f)) : 0.f;
     float tf = __fadd_rn(tc[jc], __fmul_rn(__fsub_rn(u, cdf[jc]), slope));
-    t_fine[ray * NF + k] = tf;
+    t_fine[ray * nf + k] = tf;
   }
   if (__any_sync(FULL, bad) && lane == 0) atomicOr(status, 1);
 }
 
-// backward (B.5): g_tf -> g_w.   u, idx, delta0, t_coarse carry no gradient.
+// backward (B.5): g_tf (+ g_tf2, the second gradient path into t_fine, summed on the fly) -> g_w.
+// u, idx, delta0, t_coarse carry no gradient.
+template <int EC>
 __global__ void __launch_bounds__(PDF_WARPS * 32)
-    sample_pdf_bwd_kernel(int64_t n, const float* __restrict__ t_coarse, const float* __restrict__ w,
+    sample_pdf_bwd_kernel(int64_t n, int nf, const float* __restrict__ t_coarse, const float* __restrict__ w,
                           const float* __restrict__ delta0_ptr, const float* __restrict__ g_tf,
-                          float* __restrict__ g_w) {
+                          const float* __restrict__ g_tf2, float* __restrict__ g_w) {
+  constexpr int NC = 32 * EC;
   __shared__ float s_cdf[PDF_WARPS][NC], s_w[PDF_WARPS][NC], s_gcdf[PDF_WARPS][NC], s_gslope[PDF_WARPS][NC];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ray = (int64_t)blockIdx.x * PDF_WARPS + wib;
@@ -110,55 +123,75 @@ __global__ void __launch_bounds__(PDF_WARPS * 32)
   float* wsm = s_w[wib];
   float* gcdf = s_gcdf[wib];
   float* gsl = s_gslope[wib];
-  gcdf[lane * 2] = gcdf[lane * 2 + 1] = 0.f;
-  gsl[lane * 2] = gsl[lane * 2 + 1] = 0.f;
-  float lo, hi, step;
-  build_cdf(w + ray * NC, cdf, wsm, lane, lo, hi, step);
-  const float delta0 = delta0_ptr ? *delta0_ptr : __fsub_rn(t_coarse[1], t_coarse[0]);
 #pragma unroll
-  for (int q = 0; q < NF / 32; ++q) {
+  for (int k = 0; k < EC; ++k) gcdf[lane * EC + k] = gsl[lane * EC + k] = 0.f;
+  float lo, hi, step;
+  build_cdf<EC>(w + ray * NC, cdf, wsm, lane, nf, lo, hi, step);
+  const float delta0 = delta0_ptr ? *delta0_ptr : __fsub_rn(t_coarse[1], t_coarse[0]);
+  for (int q = 0; q < nf / 32; ++q) {
     int k = q * 32 + lane;
     float u = __fadd_rn(__fmul_rn((float)(k + 1), step), lo);
-    int j = min(max(count_less(cdf, u) - 1, 0), NC - 1);
-    float g = g_tf[ray * NF + k];
+    int j = min(max(count_less<NC>(cdf, u) - 1, 0), NC - 1);
+    float g = g_tf[ray * nf + k];
+    if (g_tf2) g += g_tf2[ray * nf + k];
     float slope = (j < NC - 1) ? __fdiv_rn(delta0, __fadd_rn(wsm[j + 1], 1e-7f)) : 0.f;
     atomicAdd(&gcdf[j], -g * slope);
     if (j < NC - 1) atomicAdd(&gsl[j], g * (u - cdf[j]));
   }
   __syncwarp();
   // g_w_j = sum_{i>=j} g_cdf_i  (cumsum backward)  +  g_slope_{j-1} * (-delta0/(w_j+eps)^2)
-  float a0 = gcdf[lane * 2], a1 = gcdf[lane * 2 + 1];
-  float lsum = a0 + a1;
+  float a[EC], lsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < EC; ++k) {
+    a[k] = gcdf[lane * EC + k];
+    lsum += a[k];
+  }
   float v = lsum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     float x = __shfl_down_sync(FULL, v, o);
     if (lane + o < 32) v += x;
   }
-  float after = v - lsum;
-  float gw1 = after + a1;
-  float gw0 = gw1 + a0;
-  int j0 = lane * 2, j1 = lane * 2 + 1;
-  if (j0 > 0) {
-    float d = wsm[j0] + 1e-7f;
-    gw0 += gsl[j0 - 1] * (-delta0 / (d * d));
+  float run = v - lsum;  // lanes after this one
+#pragma unroll
+  for (int k = EC - 1; k >= 0; --k) {
+    run += a[k];
+    const int j = lane * EC + k;
+    float gw = run;
+    if (j > 0) {
+      float d = wsm[j] + 1e-7f;
+      gw += gsl[j - 1] * (-delta0 / (d * d));
+    }
+    g_w[ray * NC + j] = gw;
   }
-  {
-    float d = wsm[j1] + 1e-7f;
-    gw1 += gsl[j1 - 1] * (-delta0 / (d * d));
+}
+
+#define NT_DISPATCH_EC(NCV, CALL)                        \
+  switch ((NCV) / 32) {                                  \
+    case 1: { constexpr int E = 1; CALL; } break;        \
+    case 2: { constexpr int E = 2; CALL; } break;        \
+    case 3: { constexpr int E = 3; CALL; } break;        \
+    default: { constexpr int E = 4; CALL; } break;       \
   }
-  g_w[ray * NC + j0] = gw0;
-  g_w[ray * NC + j1] = gw1;
+
+int nt_launch_sample_pdf_backward(nt_ctx* ctx, int64_t n, const float* t_coarse, const float* w, const float* delta0,
+                                  const float* g_t_fine, const float* g_t_fine2, float* g_w, cudaStream_t st) {
+  if (n <= 0) return NT_OK;
+  const unsigned blocks = (unsigned)((n + PDF_WARPS - 1) / PDF_WARPS);
+  NT_DISPATCH_EC(ctx->n_coarse, (sample_pdf_bwd_kernel<E><<<blocks, PDF_WARPS * 32, 0, st>>>(n, ctx->n_fine, t_coarse, w, delta0,
+                                                                                            g_t_fine, g_t_fine2, g_w)));
+  NT_LAUNCH_CHECK(ctx);
+  return NT_OK;
 }
 
 extern "C" int nt_sample_pdf(nt_ctx* ctx, int64_t n, const float* t_coarse, const float* w, const float* delta0,
                              float* t_fine, int32_t* idx, void* stream) {
   NT_ENTER(ctx);
   NT_REQUIRE(ctx && t_coarse && w && t_fine, "null pointer");
-  NT_REQUIRE(ctx->n_coarse == NC && ctx->n_fine == NF, "sample_pdf is built for Nc=64, Nf=128");
   if (n <= 0) return NT_OK;
-  sample_pdf_kernel<<<(unsigned)((n + PDF_WARPS - 1) / PDF_WARPS), PDF_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      n, t_coarse, w, delta0, t_fine, idx, ctx->d_flags + 1);
+  const unsigned blocks = (unsigned)((n + PDF_WARPS - 1) / PDF_WARPS);
+  NT_DISPATCH_EC(ctx->n_coarse, (sample_pdf_kernel<E><<<blocks, PDF_WARPS * 32, 0, (cudaStream_t)stream>>>(
+                                    n, ctx->n_fine, t_coarse, w, delta0, t_fine, idx, ctx->d_flags + 1)));
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;
 }
@@ -167,12 +200,7 @@ extern "C" int nt_sample_pdf_backward(nt_ctx* ctx, int64_t n, const float* t_coa
                                       const float* delta0, const float* g_t_fine, float* g_w, void* stream) {
   NT_ENTER(ctx);
   NT_REQUIRE(ctx && t_coarse && w && g_t_fine && g_w, "null pointer");
-  NT_REQUIRE(ctx->n_coarse == NC && ctx->n_fine == NF, "sample_pdf is built for Nc=64, Nf=128");
-  if (n <= 0) return NT_OK;
-  sample_pdf_bwd_kernel<<<(unsigned)((n + PDF_WARPS - 1) / PDF_WARPS), PDF_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      n, t_coarse, w, delta0, g_t_fine, g_w);
-  NT_LAUNCH_CHECK(ctx);
-  return NT_OK;
+  return nt_launch_sample_pdf_backward(ctx, n, t_coarse, w, delta0, g_t_fine, nullptr, g_w, (cudaStream_t)stream);
 }
 
 extern "C" int nt_check_status(nt_ctx* ctx, void* stream) {
