@@ -45,6 +45,8 @@ extern "C" {
 #define NT_PREC_BF16 2 /* bf16 operands, fp32 accumulate, tcgen05/TMEM fused kernels: forward + backward (training)   */
 #define NT_PREC_FP16 3 /* fp16 operands (saturating), fp32 accumulate: same kernels and speed as BF16 with 8x smaller */
                        /* operand rounding (the network's activations are bounded); rendering (forward) only          */
+#define NT_PREC_MIXED 4 /* rendering: the coarse pass (n_coarse samples per ray, whose weights steer the resampling) in  */
+                        /* NT_PREC_TC32 arithmetic, the fine pass in NT_PREC_FP16                                      */
 
 #define NT_N_LAYERS 12
 #define NT_N_PARAMS 593924

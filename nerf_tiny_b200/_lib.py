@@ -17,6 +17,7 @@ PREC_FP32 = 0
 PREC_TC32 = 1
 PREC_BF16 = 2
 PREC_FP16 = 3
+PREC_MIXED = 4
 ANY_STEP_ZERO_DEVICE = -2
 OPT_DETACH_T_FINE = 1
 OPT_MLP_TC_VERSION = 2

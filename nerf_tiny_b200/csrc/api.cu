@@ -109,19 +109,22 @@ extern "C" int nt_set_option(nt_ctx* ctx, int key, int value) {
 // ---- precision dispatch ------------------------------------------------------------------------
 static bool is_tc16(int precision) { return precision == NT_PREC_BF16 || precision == NT_PREC_FP16; }
 static bool known_precision(int precision) {
-  return precision == NT_PREC_FP32 || precision == NT_PREC_TC32 || is_tc16(precision);
+  return precision == NT_PREC_FP32 || precision == NT_PREC_TC32 || precision == NT_PREC_MIXED || is_tc16(precision);
 }
+// NT_PREC_MIXED packs both operand images: [split-fp16 image (coarse pass) | fp16 image (fine pass)]
+static size_t mixed_fp16_offset() { return (nt_mlp_tc32_packed_bytes() + 1023) & ~(size_t)1023; }
 
 extern "C" size_t nt_mlp_workspace_bytes(nt_ctx* ctx, int precision, int64_t n, int p, int train) {
   (void)ctx;
   if (precision == NT_PREC_FP32) return nt_mlp_f32_workspace_bytes(n, p, train);
   if (precision == NT_PREC_BF16) return train ? nt_mlp_bf16_train_workspace_bytes(n, p) : 256;
-  if (precision == NT_PREC_FP16 || precision == NT_PREC_TC32) return train ? 0 : 256;  // rendering modes
+  if (precision == NT_PREC_FP16 || precision == NT_PREC_TC32 || precision == NT_PREC_MIXED) return train ? 0 : 256;  // rendering modes
   return 0;
 }
 extern "C" size_t nt_packed_weight_bytes(nt_ctx* ctx, int precision) {
   (void)ctx;
   if (is_tc16(precision)) return nt_mlp_tc_packed_bytes();
+  if (precision == NT_PREC_MIXED) return mixed_fp16_offset() + nt_mlp_tc_packed_bytes();
   return precision == NT_PREC_TC32 ? nt_mlp_tc32_packed_bytes() : 0;
 }
 extern "C" int nt_pack_weights(nt_ctx* ctx, int precision, const float* params, void* packed, void* stream) {
@@ -129,6 +132,11 @@ extern "C" int nt_pack_weights(nt_ctx* ctx, int precision, const float* params, 
   NT_REQUIRE(ctx && params, "null pointer");
   if (precision == NT_PREC_FP32) return NT_OK;
   NT_REQUIRE(known_precision(precision) && packed, "bad precision / null packed buffer");
+  if (precision == NT_PREC_MIXED) {
+    int rc = nt_mlp_tc_pack(ctx, params, packed, 2, (cudaStream_t)stream);
+    if (rc != NT_OK) return rc;
+    return nt_mlp_tc_pack(ctx, params, (char*)packed + mixed_fp16_offset(), 1, (cudaStream_t)stream);
+  }
   const int mode = precision == NT_PREC_BF16 ? 0 : (precision == NT_PREC_FP16 ? 1 : 2);
   return nt_mlp_tc_pack(ctx, params, packed, mode, (cudaStream_t)stream);
 }
@@ -151,12 +159,19 @@ extern "C" int nt_mlp_forward(nt_ctx* ctx, int precision, int64_t n, int p, cons
   NT_REQUIRE(packed, "the tensor-core precisions need packed weights (nt_pack_weights with the same precision)");
   if (train) {  // fused tcgen05 forward + bf16 activation stash for the tensor-core backward
     if (precision != NT_PREC_BF16) {
-      nt_set_error("NT_PREC_FP16 / NT_PREC_TC32 are rendering modes; train with NT_PREC_BF16 or NT_PREC_FP32");
+      nt_set_error("NT_PREC_FP16 / NT_PREC_TC32 / NT_PREC_MIXED are rendering modes; train with NT_PREC_BF16 or NT_PREC_FP32");
       return NT_ERR_UNSUPPORTED;
     }
     NT_REQUIRE(ws, "bf16 training needs a workspace");
     return nt_mlp_bf16_train_forward(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, ws, ws_bytes,
                                      (cudaStream_t)stream);
+  }
+  if (precision == NT_PREC_MIXED) {
+    // the pass over the COARSE samples decides where the fine samples go (resample amplifies its errors):
+    // coarse-sized passes (p == n_coarse) run split-fp16, everything else single-pass fp16
+    if (p == ctx->n_coarse) return nt_mlp_tc32_forward(ctx, n, p, t, rays, dir_enc, packed, rgb, sigma, (cudaStream_t)stream);
+    return nt_mlp_tc_forward(ctx, n, p, t, rays, dir_enc, params, (const char*)packed + mixed_fp16_offset(), rgb, sigma, 1,
+                             (cudaStream_t)stream);
   }
   if (precision == NT_PREC_TC32) return nt_mlp_tc32_forward(ctx, n, p, t, rays, dir_enc, packed, rgb, sigma, (cudaStream_t)stream);
   return nt_mlp_tc_forward(ctx, n, p, t, rays, dir_enc, params, packed, rgb, sigma, precision == NT_PREC_FP16 ? 1 : 0,

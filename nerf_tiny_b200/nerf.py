@@ -32,8 +32,11 @@ device = None
 # finer than bf16 at the same speed; the network's activations are bounded, so fp16 is the default for rendering);
 # "tc32": 3-pass split-fp16 tcgen05 kernel meeting the fp32 tolerance on the tensor cores; "fp32": CUDA-core FFMA.
 # Training runs on the bf16 tensor-core path for "bf16" / "fp16" and on the fp32 path for "fp32" / "tc32".
-PRECISION = {"fp32": _lib.PREC_FP32, "tc32": _lib.PREC_TC32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
-TRAIN_PRECISION = {"fp32": _lib.PREC_FP32, "tc32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_BF16}
+# "mixed": coarse pass in tc32 arithmetic (its weights steer the resampling, which amplifies their errors), fine pass fp16.
+PRECISION = {"fp32": _lib.PREC_FP32, "tc32": _lib.PREC_TC32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16,
+             "mixed": _lib.PREC_MIXED}
+TRAIN_PRECISION = {"fp32": _lib.PREC_FP32, "tc32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_BF16,
+                   "mixed": _lib.PREC_BF16}
 DEFAULT_PRECISION = "fp16"
 
 
