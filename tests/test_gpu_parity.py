@@ -13,7 +13,7 @@ from oracle import nerf_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["kat8", "lego48", "lego48_trained", "fern64", "fern64_trained", "trained64"]
+CASES = ["kat8", "lego48", "lego48_trained", "fern64", "fern64_trained", "trained64", "trained2k5"]
 FP32, BF16 = 0, 2
 
 
@@ -24,8 +24,10 @@ def bits(a):
 
 
 def sd_of(case):
-    if case == "trained64":      # weights the reference itself trained (oracle/make_trained_golden.py), stored as fp16
-        z = np.load(os.path.join(os.path.dirname(__file__), "golden", "trained_weights_fp16.npz"))
+    if case in ("trained64", "trained2k5"):   # weights the reference itself trained (oracle/make_trained_golden.py: 250 and
+        # 2 500 steps), stored as fp16
+        name = "trained_weights_fp16.npz" if case == "trained64" else case + "_weights_fp16.npz"
+        z = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
         return {k: torch.from_numpy(z[k].astype(np.float32)) for k in z.files if not k.startswith("__")}
     sd = O.init_state_dict(624)
     return O.trained_like(sd) if case.endswith("trained") else sd
@@ -288,6 +290,8 @@ def test_forward_fp32_matches_reference(dev, golden_dir, case):
     with torch.no_grad():
         cc, cf = m(torch.from_numpy(g["row"]), torch.from_numpy(g["col"]), torch.from_numpy(g["poses_bound"]),
                    torch.from_numpy(g["k_inv"]))
+    print(case, "fp32 max-abs err  C_coarse %.2e  C_fine %.2e" % (np.abs(cc.cpu().numpy() - g["c_coarse"]).max(),
+                                                                  np.abs(cf.cpu().numpy() - g["c_fine"]).max()))
     assert np.abs(cc.cpu().numpy() - g["c_coarse"]).max() <= 1e-3      # north_star fp32 tolerance
     assert np.abs(cf.cpu().numpy() - g["c_fine"]).max() <= 1e-3
     assert np.abs(cc.cpu().numpy() - g["c_coarse"]).max() <= 5e-5      # what we actually hold
