@@ -77,6 +77,10 @@ int nt_layer_table(nt_layer_desc out[NT_N_LAYERS]);
 #define NT_OPT_DETACH_T_FINE 1
 #define NT_OPT_MLP_TC_VERSION 2
 #define NT_OPT_LAST_DELTA 3
+/* NT_OPT_DW_OVERLAP_CTAS (training, NT_PREC_BF16; 0 = off): nt_render_backward launches the HBM-bound weight-gradient
+ * contraction of the fine pass on an internal side stream, capped to this many CTAs, so that it overlaps the MMA-bound
+ * backward of the coarse pass (which runs on the remaining SMs); joined again before the call's last launch. */
+#define NT_OPT_DW_OVERLAP_CTAS 4
 int nt_set_option(nt_ctx* ctx, int key, int value);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t nt_launch_count(const nt_ctx* ctx);

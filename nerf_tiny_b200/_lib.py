@@ -22,6 +22,7 @@ ANY_STEP_ZERO_DEVICE = -2
 OPT_DETACH_T_FINE = 1
 OPT_MLP_TC_VERSION = 2
 OPT_LAST_DELTA = 3
+OPT_DW_OVERLAP_CTAS = 4
 N_PARAMS = 593924
 N_LAYERS = 12
 

@@ -1,6 +1,7 @@
 // C-ABI glue: context, error reporting, precision dispatch and the fused render drivers
 // (render_rays nerf.py:286-323 forward; SURVEY.md §3.5 order for backward).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -64,11 +65,28 @@ extern "C" int nt_create(nt_ctx** out, int device, int n_coarse, int n_fine) {
   c->opt_detach_t_fine = 0;
   c->opt_tc_version = 0;
   c->attr_done = 0;
+  c->side = nullptr;
+  c->ev_fork = c->ev_join = nullptr;
+  c->defer_dw = c->dw_pending = 0;
+  {
+    // measured on B200 (1024 / 4096 rays per step, gpurun_out/r2j_sweep*.log): 0 -> 1.508 / 5.133 ms, 72 -> 1.480 / 5.208,
+    // 88 -> 1.466 / 5.003 (best), 96 -> 1.472 / 5.123, 112 -> 1.668 / 5.669: the HBM-bound launch needs ~60 % of the SMs
+    const char* e = getenv("NT_DW_OVERLAP_CTAS");
+    c->opt_dw_overlap_ctas = e ? atoi(e) : (c->sm_count * 88) / 148;
+    if (c->opt_dw_overlap_ctas < 0 || c->opt_dw_overlap_ctas >= c->sm_count) c->opt_dw_overlap_ctas = 0;
+  }
   c->last_delta = 1e-4f;
   c->d_flags = nullptr;
   if (cudaMalloc(&c->d_flags, 4 * sizeof(int)) != cudaSuccess || cudaMemset(c->d_flags, 0, 4 * sizeof(int)) != cudaSuccess) {
     nt_set_error("cudaMalloc of the status flags failed");
     delete c;
+    return NT_ERR_CUDA;
+  }
+  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    nt_set_error("creating the side stream / events failed");
+    nt_destroy(c);
     return NT_ERR_CUDA;
   }
   *out = c;
@@ -79,6 +97,9 @@ extern "C" void nt_destroy(nt_ctx* ctx) {
   if (!ctx) return;
   NT_ENTER(ctx);
   if (ctx->d_flags) cudaFree(ctx->d_flags);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
   delete ctx;
 }
 
@@ -93,6 +114,11 @@ extern "C" int nt_set_option(nt_ctx* ctx, int key, int value) {
   if (key == NT_OPT_MLP_TC_VERSION) {
     NT_REQUIRE(value == 0 || value == 5 || value == 7, "mlp_tc version must be 0 (default), 5 or 7");
     ctx->opt_tc_version = value;
+    return NT_OK;
+  }
+  if (key == NT_OPT_DW_OVERLAP_CTAS) {
+    NT_REQUIRE(value >= 0 && value < ctx->sm_count, "dW overlap CTAs must be in [0, SM count)");
+    ctx->opt_dw_overlap_ctas = value;
     return NT_OK;
   }
   if (key == NT_OPT_LAST_DELTA) {
@@ -302,8 +328,11 @@ extern "C" int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const f
                                     w.g_rgb_c, w.g_sig_c, w.g_rgb_f, w.g_sig_f, w.g_t_f, stream));
   // fine MLP: dW + input gradient down to t_fine (B.4, B.6, B.7)
   const bool detach = ctx->opt_detach_t_fine != 0;
-  NT_TRY(nt_mlp_backward(ctx, precision, n, nf, w.t_f, w.rays, w.dir_enc, params, packed, w.rgb_f, w.g_rgb_f, w.g_sig_f, grads,
-                         detach ? nullptr : w.g_t_mlp, w.mlp_f, w.mlp_f_bytes, stream));
+  ctx->defer_dw = (precision == NT_PREC_BF16 && ctx->opt_dw_overlap_ctas > 0) ? 1 : 0;
+  int rc_fine = nt_mlp_backward(ctx, precision, n, nf, w.t_f, w.rays, w.dir_enc, params, packed, w.rgb_f, w.g_rgb_f, w.g_sig_f, grads,
+                                detach ? nullptr : w.g_t_mlp, w.mlp_f, w.mlp_f_bytes, stream);
+  ctx->defer_dw = 0;
+  NT_TRY(rc_fine);
   // g_t_fine = compositing path + MLP-input path (summed inside the kernel); then resample backward (B.5)
   if (!detach)
     NT_TRY(nt_launch_sample_pdf_backward(ctx, n, w.t_c, w.w_c, delta0, w.g_t_f, w.g_t_mlp, w.g_w_c, (cudaStream_t)stream));
@@ -313,6 +342,7 @@ extern "C" int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const f
   // coarse MLP: dW only (t_coarse is a constant)
   NT_TRY(nt_mlp_backward(ctx, precision, n, nc, w.t_c, w.rays, w.dir_enc, params, packed, w.rgb_c, w.g_rgb_c, w.g_sig_c, grads,
                          nullptr, w.mlp_c, w.mlp_c_bytes, stream));
+  NT_TRY(nt_join_deferred_dw(ctx, (cudaStream_t)stream));
   return NT_OK;
 }
 

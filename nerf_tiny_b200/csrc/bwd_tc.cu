@@ -336,7 +336,7 @@ int nt_bwd_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t 
 
 // g_u bf16 [S][128] -> outs[0] = g_info, outs[1..8] = g_7 .. g_0 (bf16 [S][256] each); db[k] accumulates colsum(outs[k])
 int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9], const int out_ld[9], const void* packed,
-                    const uint32_t* bits,
+                    int max_ctas, const uint32_t* bits,
                     const float* gzsig, const float* wsig, float* const db[9], cudaStream_t st) {
   if (S <= 0) return NT_OK;
   if (!(ctx->attr_done & NT_ATTR_BWD_TC)) {
@@ -359,7 +359,8 @@ int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9]
   P.total = S;
   const int64_t tiles = (S + TILE_M - 1) / TILE_M;
   P.num_pairs = (int)((tiles + 1) / 2);
-  const int grid = ctx->sm_count < P.num_pairs ? ctx->sm_count : P.num_pairs;
+  int grid = ctx->sm_count < P.num_pairs ? ctx->sm_count : P.num_pairs;
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;  // leave SMs to a concurrent launch on another stream
   bwd_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;

@@ -22,6 +22,13 @@ struct nt_ctx {
   int opt_detach_t_fine;
   int opt_tc_version;
   float last_delta;    // delta of the last merged sample (render_rays `last`, nerf.py:286, :311); default 1e-4
+  // training: the HBM-bound weight-gradient launch of the FINE pass can run on `side`, capped to opt_dw_overlap_ctas CTAs,
+  // next to the MMA-bound backward of the coarse pass (fork / join by events, capturable into a CUDA graph)
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  int opt_dw_overlap_ctas;  // 0 = off
+  int defer_dw;             // set by nt_render_backward around the fine pass
+  int dw_pending;           // a deferred launch has not been joined yet
   unsigned attr_done;  // NT_ATTR_*: cudaFuncSetAttribute is per DEVICE, so the "already opted in" bits live in the ctx
 };
 enum {
@@ -197,6 +204,7 @@ int nt_mlp_tc_forward_stash(nt_ctx* ctx, int64_t n, int p, const float* t, const
                             const float* params, const void* packed, float* rgb, float* sigma, const TcStash* stash,
                             cudaStream_t st);
 // train_bf16.cu
+int nt_join_deferred_dw(nt_ctx* ctx, cudaStream_t st);
 size_t nt_mlp_bf16_train_workspace_bytes(int64_t n, int p);
 int nt_mlp_bf16_train_forward(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                               const float* params, const void* packed, float* rgb, float* sigma, void* ws, size_t ws_bytes,
@@ -209,11 +217,11 @@ int nt_launch_dw_gemm(nt_ctx* ctx, int S, const void* G, int ldg, int m_valid, c
 // grouped weight-gradient GEMM: queue problems of one backward pass (all with the same sample count S), flush once
 int nt_dw_group_begin(int S);
 int nt_dw_group_add(const void* G, int ldg, int m_valid, const void* H, int ldh, int n_valid, float* C, int ldc);
-int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st);
+int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st, int max_ctas /*0 = all SMs*/);
 int nt_make_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);
 // bwd_tc.cu — fused backward-data chain
 size_t nt_bwd_tc_packed_bytes();
 int nt_bwd_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t st);
 int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9], const int out_ld[9], const void* packed,
-                    const uint32_t* bits,
+                    int max_ctas, const uint32_t* bits,
                     const float* gzsig, const float* wsig, float* const db[9], cudaStream_t st);

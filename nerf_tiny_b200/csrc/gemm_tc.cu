@@ -483,6 +483,9 @@ struct DwGroup {
   int S;
 };
 
+// Persistent: a CTA walks work items blockIdx.x, blockIdx.x + gridDim.x, ... (item = one problem's K-split); the TMA
+// producer runs ahead into the next item's sample blocks while the epilogue warps drain the accumulator, and the grid can
+// be capped so that the launch shares the GPU with an MMA-bound kernel on another stream (train_bf16.cu).
 __global__ void __launch_bounds__(GEMM_THREADS, 1) dw_grouped_kernel(const __grid_constant__ DwGroup g) {
   constexpr int BN = 256;
   constexpr int B_BYTES = BN * 128;
@@ -491,17 +494,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dw_grouped_kernel(const __gri
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };  // full[3] 0-2, empty[3] 3-5, acc_full 6
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };  // full[3] 0-2, empty[3] 3-5, acc_full 6, acc_empty 7
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
-  int pr = 0;
-  while (pr + 1 < g.n_problems && (int)blockIdx.x >= g.cta_begin[pr + 1]) ++pr;
-  const int slot = blockIdx.x - g.cta_begin[pr];
+  const int n_items = g.cta_begin[g.n_problems];
   const int kb_total = (g.S + BK - 1) / BK;  // rows past S are zero-filled by TMA: a partial last block adds nothing
-  const int kb0 = slot * g.kb_per_cta[pr];
-  const int kb1 = min(kb_total, kb0 + g.kb_per_cta[pr]);
-  const int m_valid = g.m_valid[pr], n_valid = g.n_valid[pr];
-  const int a_boxes = (m_valid + 63) / 64, b_boxes = (n_valid + 63) / 64;  // boxes that are not entirely out of range
-  const bool two_m = m_valid > 128;
+  constexpr int N_EPI_WARPS = GEMM_THREADS / 32 - 2;
 
   if (threadIdx.x == 0) {
     if (sbase & 1023) __trap();
@@ -510,6 +507,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dw_grouped_kernel(const __gri
       mbar_init(bar(3 + s), 1);
     }
     mbar_init(bar(6), 1);
+    mbar_init(bar(7), N_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -521,55 +519,87 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dw_grouped_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // item -> (problem, K range); evaluated identically by every role
+  auto locate = [&](int item, int& pr, int& kb0, int& kb1) {
+    pr = 0;
+    while (pr + 1 < g.n_problems && item >= g.cta_begin[pr + 1]) ++pr;
+    kb0 = (item - g.cta_begin[pr]) * g.kb_per_cta[pr];
+    kb1 = min(kb_total, kb0 + g.kb_per_cta[pr]);
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       uint32_t q = 0;
-      for (int kb = kb0; kb < kb1; ++kb, ++q) {
-        const uint32_t s = q % DW_STAGES;
-        mbar_wait(bar(3 + s), ((q / DW_STAGES) & 1) ^ 1);
-        mbar_expect_tx(bar(s), (a_boxes + b_boxes) * 8192);
-        const uint32_t da = sbase + s * STAGE, db = da + DW_A_BYTES;
-        for (int b = 0; b < a_boxes; ++b) tma_load_2d(da + b * 8192, &g.map_a[pr], b * 64, kb * BK, bar(s));
-        for (int b = 0; b < b_boxes; ++b) tma_load_2d(db + b * 8192, &g.map_b[pr], b * 64, kb * BK, bar(s));
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int pr, kb0, kb1;
+        locate(item, pr, kb0, kb1);
+        const int a_boxes = (g.m_valid[pr] + 63) / 64, b_boxes = (g.n_valid[pr] + 63) / 64;  // boxes not entirely out of range
+        for (int kb = kb0; kb < kb1; ++kb, ++q) {
+          const uint32_t s = q % DW_STAGES;
+          mbar_wait(bar(3 + s), ((q / DW_STAGES) & 1) ^ 1);
+          mbar_expect_tx(bar(s), (a_boxes + b_boxes) * 8192);
+          const uint32_t da = sbase + s * STAGE, db = da + DW_A_BYTES;
+          for (int b = 0; b < a_boxes; ++b) tma_load_2d(da + b * 8192, &g.map_a[pr], b * 64, kb * BK, bar(s));
+          for (int b = 0; b < b_boxes; ++b) tma_load_2d(db + b * 8192, &g.map_b[pr], b * 64, kb * BK, bar(s));
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // N of the instruction = the columns that exist (multiple of 64): columns beyond were never loaded
-      const uint32_t idesc = idesc_bf16(b_boxes * 64, true);
-      uint32_t q = 0;
-      for (int kb = kb0; kb < kb1; ++kb, ++q) {
-        const uint32_t s = q % DW_STAGES;
-        mbar_wait(bar(s), (q / DW_STAGES) & 1);
+      uint32_t q = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        int pr, kb0, kb1;
+        locate(item, pr, kb0, kb1);
+        const int b_boxes = (g.n_valid[pr] + 63) / 64;
+        const bool two_m = g.m_valid[pr] > 128;
+        // N of the instruction = the columns that exist (multiple of 64): columns beyond were never loaded
+        const uint32_t idesc = idesc_bf16(b_boxes * 64, true);
+        mbar_wait(bar(7), (it & 1) ^ 1);  // the previous item's accumulator has been drained
         tc_fence_after();
-        const uint32_t a_addr = sbase + s * STAGE, b_addr = a_addr + DW_A_BYTES;
+        for (int kb = kb0; kb < kb1; ++kb, ++q) {
+          const uint32_t s = q % DW_STAGES;
+          mbar_wait(bar(s), (q / DW_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = sbase + s * STAGE, b_addr = a_addr + DW_A_BYTES;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint64_t bd = desc_mnmajor(b_addr + j * 2048, 8192);
-          const uint32_t acc = (kb > kb0 || j > 0) ? 1u : 0u;
-          umma_bf16(tmem_base, desc_mnmajor(a_addr + j * 2048, 8192), bd, idesc, acc);
-          if (two_m) umma_bf16(tmem_base + 256, desc_mnmajor(a_addr + 16384 + j * 2048, 8192), bd, idesc, acc);
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t bd = desc_mnmajor(b_addr + j * 2048, 8192);
+            const uint32_t acc = (kb > kb0 || j > 0) ? 1u : 0u;
+            umma_bf16(tmem_base, desc_mnmajor(a_addr + j * 2048, 8192), bd, idesc, acc);
+            if (two_m) umma_bf16(tmem_base + 256, desc_mnmajor(a_addr + 16384 + j * 2048, 8192), bd, idesc, acc);
+          }
+          umma_commit(bar(3 + s));
         }
-        umma_commit(bar(3 + s));
+        umma_commit(bar(6));
       }
-      umma_commit(bar(6));
     }
-  } else if (kb1 > kb0) {
+  } else {
     const int e = warp - 2, quad = warp & 3, half = e >> 2;
-    mbar_wait(bar(6), 0);
-    tc_fence_after();
-    float* Cp = g.C[pr];
-    const int ldc = g.ldc[pr];
-    for (int mt = 0; mt < (two_m ? 2 : 1); ++mt) {
-      const int m = mt * 128 + quad * 32 + lane;
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + mt * 256;
-      for (int i = 0; i < 4; ++i) {
-        const int n0 = (half * 4 + i) * 32;
-        if (n0 >= b_boxes * 64) continue;  // warp-uniform: these columns were not computed
-        uint32_t raw[32];
-        tmem_ld32(trow + n0, raw);
-        if (m < m_valid && n0 < n_valid) red_add_32(Cp + (int64_t)m * ldc + n0, raw, n_valid - n0);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      int pr, kb0, kb1;
+      locate(item, pr, kb0, kb1);
+      const int m_valid = g.m_valid[pr], n_valid = g.n_valid[pr];
+      const int b_boxes = (n_valid + 63) / 64;
+      const bool two_m = m_valid > 128;
+      mbar_wait(bar(6), it & 1);
+      tc_fence_after();
+      float* Cp = g.C[pr];
+      const int ldc = g.ldc[pr];
+      for (int mt = 0; mt < (two_m ? 2 : 1); ++mt) {
+        const int m = mt * 128 + quad * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + mt * 256;
+        for (int i = 0; i < 4; ++i) {
+          const int n0 = (half * 4 + i) * 32;
+          if (n0 >= b_boxes * 64) continue;  // warp-uniform: these columns were not computed
+          uint32_t raw[32];
+          tmem_ld32(trow + n0, raw);
+          if (m < m_valid && n0 < n_valid) red_add_32(Cp + (int64_t)m * ldc + n0, raw, n_valid - n0);
+        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(7));
     }
   }
   __syncwarp();
@@ -767,7 +797,7 @@ int nt_dw_group_add(const void* G, int ldg, int m_valid, const void* H, int ldh,
   return NT_OK;
 }
 
-int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st) {
+int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st, int max_ctas) {
   DwGroup& g = g_dwq.g;
   if (g.n_problems == 0) return NT_OK;
   const int kb_total = (g.S + BK - 1) / BK;  // rows past S are zero-filled by TMA: a partial last block adds nothing
@@ -790,7 +820,10 @@ int nt_dw_group_flush(nt_ctx* ctx, cudaStream_t st) {
     NT_CUDA(cudaFuncSetAttribute(dw_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ctx->attr_done |= NT_ATTR_DW_GROUPED;
   }
-  dw_grouped_kernel<<<begin, GEMM_THREADS, smem, st>>>(g);
+  int grid = ctx->sm_count;  // persistent: one CTA per SM walks the ~2 items per SM
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (grid > begin) grid = begin;
+  dw_grouped_kernel<<<grid, GEMM_THREADS, smem, st>>>(g);
   NT_LAUNCH_CHECK(ctx);
   g.n_problems = 0;
   return NT_OK;

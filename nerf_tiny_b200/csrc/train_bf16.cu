@@ -271,7 +271,11 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
     float* dbs[9] = {G + T.b[L_INFO], G + T.b[L_P7], G + T.b[L_P6], G + T.b[L_P5], G + T.b[L_P4],
                      G + T.b[L_P3],   G + T.b[L_P2], G + T.b[L_P1], G + T.b[L_P0]};
     const int lds[9] = {256, w.ldgs[7], w.ldgs[6], w.ldgs[5], w.ldgs[4], w.ldgs[3], w.ldgs[2], w.ldgs[1], w.ldgs[0]};
-    NT_TRY(nt_bwd_tc_chain(ctx, S, w.Gu, outs, lds, w.WB, w.st.bits, w.gzsig, P + T.w[L_SIGMA], dbs, st));
+    // while a deferred weight-gradient launch of the previous pass is still running on the side stream, this MMA-bound
+    // kernel takes only the SMs that launch leaves free
+    const int cap = ctx->dw_pending ? ctx->sm_count - ctx->opt_dw_overlap_ctas : 0;
+    NT_TRY(nt_bwd_tc_chain(ctx, S, w.Gu, outs, lds, w.WB, cap, w.st.bits, w.gzsig, P + T.w[L_SIGMA], dbs, st));
+    if (ctx->defer_dw) NT_CUDA(cudaEventRecord(ctx->ev_fork, st));  // every operand of this pass's dW problems is complete here
   }
   // weight gradients (queued): point_info, sigma head, trunk
   NT_TRY(dW(w.GI, 256, 256, H[7], 256, 256, G + T.w[L_INFO], 256));
@@ -291,6 +295,24 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
     NT_TRY(nt_launch_gemm_tc(ctx, 0, S, 64, 512, w.GS[4], 512, w.WT, 512, e, st));
     NT_TRY(nt_launch_encode_backward(ctx, n, p, t, rays, w.genc, 64, g_t, st));
   }
-  NT_TRY(nt_dw_group_flush(ctx, st));
+  if (ctx->defer_dw) {
+    // fork: the HBM-bound contraction of this (fine) pass runs on the side stream with a capped grid, next to the
+    // coarse pass's backward on `st`; nt_join_deferred_dw() orders the rest of `st` behind it
+    NT_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    NT_TRY(nt_dw_group_flush(ctx, ctx->side, ctx->opt_dw_overlap_ctas));
+    NT_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+    ctx->dw_pending = 1;
+    return NT_OK;
+  }
+  NT_TRY(nt_join_deferred_dw(ctx, st));  // one weight-gradient launch at a time: both are HBM-bound
+  NT_TRY(nt_dw_group_flush(ctx, st, 0));
+  return NT_OK;
+}
+
+int nt_join_deferred_dw(nt_ctx* ctx, cudaStream_t st) {
+  if (ctx->dw_pending) {
+    NT_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    ctx->dw_pending = 0;
+  }
   return NT_OK;
 }
