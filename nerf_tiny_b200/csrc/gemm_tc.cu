@@ -21,6 +21,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int NSTAGE = 4;
+__host__ __device__ constexpr int gemm_stages(int bn) { return bn == 64 ? 8 : NSTAGE; }
 constexpr int A_STAGE_BYTES = BM * 128;
 constexpr int GEMM_THREADS = 320;  // warp 0 = TMA, warp 1 = MMA, warps 2-9 = epilogue
 
@@ -100,15 +101,17 @@ template <int BN, bool MN_MAJOR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmTcArgs g) {
   constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int NST = gemm_stages(BN);  // ring depth: 8 stages for the narrow (BN = 64) shape, 4 otherwise
   constexpr int OFF_A = 0;
-  constexpr int OFF_B = NSTAGE * A_STAGE_BYTES;
-  constexpr int OFF_BAR = OFF_B + NSTAGE * B_STAGE_BYTES;
+  constexpr int OFF_B = NST * A_STAGE_BYTES;
+  constexpr int OFF_BAR = OFF_B + NST * B_STAGE_BYTES;
+  constexpr int B_EMPTY = NST, B_ACCF = 2 * NST, B_ACCE = 2 * NST + 2, B_BFULL = 2 * NST + 4;  // barrier slots
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // barriers: full[4] 0-3, empty[4] 4-7, acc_full[2] 8-9, acc_empty[2] 10-11, b_full 12
+  // barriers: full[NST], empty[NST], acc_full[2], acc_empty[2], b_full
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 112);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (B_BFULL + 1));
 
   const int m_tiles = (g.M + BM - 1) / BM;
   const int kb_total = g.K / BK;
@@ -116,15 +119,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   if (threadIdx.x == 0) {
     if (sbase & 1023) __trap();
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(bar(s), 1);
-      mbar_init(bar(4 + s), 1);
+      mbar_init(bar(B_EMPTY + s), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar(8 + s), 1);
-      mbar_init(bar(10 + s), 256);
+      mbar_init(bar(B_ACCF + s), 1);
+      mbar_init(bar(B_ACCE + s), 256);
     }
-    mbar_init(bar(12), 1);
+    mbar_init(bar(B_BFULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -146,20 +149,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int kb0 = sp * g.kb_per_split;
         const int kb1 = min(kb_total, kb0 + g.kb_per_split);
         if (g.b_resident && !b_loaded) {
-          mbar_expect_tx(bar(12), kb_total * B_STAGE_BYTES);
+          mbar_expect_tx(bar(B_BFULL), kb_total * B_STAGE_BYTES);
           for (int kb = 0; kb < kb_total; ++kb) {
             const uint32_t dst = sbase + OFF_B + kb * B_STAGE_BYTES;
             if (MN_MAJOR) {
-              for (int b = 0; b < BN / 64; ++b) tma_load_2d(dst + b * 8192, &map_b, b * 64, kb * BK, bar(12));
+              for (int b = 0; b < BN / 64; ++b) tma_load_2d(dst + b * 8192, &map_b, b * 64, kb * BK, bar(B_BFULL));
             } else {
-              tma_load_2d(dst, &map_b, kb * BK, 0, bar(12));
+              tma_load_2d(dst, &map_b, kb * BK, 0, bar(B_BFULL));
             }
           }
           b_loaded = true;
         }
         for (int kb = kb0; kb < kb1; ++kb, ++q) {
-          const uint32_t s = q % NSTAGE;
-          mbar_wait(bar(4 + s), ((q / NSTAGE) & 1) ^ 1);
+          const uint32_t s = q % NST;
+          mbar_wait(bar(B_EMPTY + s), ((q / NST) & 1) ^ 1);
           mbar_expect_tx(bar(s), A_STAGE_BYTES + (g.b_resident ? 0 : B_STAGE_BYTES));
           const uint32_t da = sbase + OFF_A + s * A_STAGE_BYTES;
           if (MN_MAJOR) {
@@ -190,16 +193,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int kb0 = sp * g.kb_per_split;
         const int kb1 = min(kb_total, kb0 + g.kb_per_split);
         const uint32_t as = it & 1;  // accumulator stage
-        mbar_wait(bar(10 + as), ((it >> 1) & 1) ^ 1);  // epilogue drained this TMEM stage
+        mbar_wait(bar(B_ACCE + as), ((it >> 1) & 1) ^ 1);  // epilogue drained this TMEM stage
         tc_fence_after();
         if (g.b_resident && !b_ready) {
-          mbar_wait(bar(12), 0);
+          mbar_wait(bar(B_BFULL), 0);
           b_ready = true;
         }
         const uint32_t d_tmem = tmem_base + as * 256;
         for (int kb = kb0; kb < kb1; ++kb, ++q) {
-          const uint32_t s = q % NSTAGE;
-          mbar_wait(bar(s), (q / NSTAGE) & 1);
+          const uint32_t s = q % NST;
+          mbar_wait(bar(s), (q / NST) & 1);
           tc_fence_after();
           const uint32_t a_addr = sbase + OFF_A + s * A_STAGE_BYTES;
           const uint32_t b_addr = sbase + OFF_B + (g.b_resident ? kb : s) * B_STAGE_BYTES;
@@ -215,9 +218,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
             umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
           }
-          umma_commit(bar(4 + s));
+          umma_commit(bar(B_EMPTY + s));
         }
-        umma_commit(bar(8 + as));
+        umma_commit(bar(B_ACCF + as));
       }
     }
   } else {
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) mpre[i][qd] = __ldg(mk + i * 4 + qd);
       }
-      mbar_wait(bar(8 + as), (it >> 1) & 1);
+      mbar_wait(bar(B_ACCF + as), (it >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 256;
 #pragma unroll
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
       }
       tc_fence_before();
-      mbar_arrive(bar(10 + as));
+      mbar_arrive(bar(B_ACCE + as));
     }
   }
   __syncwarp();
@@ -651,7 +654,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
 
 template <int BN, bool MN>
 int launch(nt_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const GemmTcArgs& g, cudaStream_t st) {
-  constexpr int smem = NSTAGE * A_STAGE_BYTES + NSTAGE * BN * 128 + 128;
+  constexpr int smem = gemm_stages(BN) * (A_STAGE_BYTES + BN * 128) + 256;
   static bool set[NT_MAX_DEVICES] = {};  // the opt-in is per device (and per template instantiation)
   if (!set[ctx->device]) {
     NT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -702,7 +705,7 @@ int nt_launch_gemm_tc(nt_ctx* ctx, int mn_major, int M, int N, int K, const void
   }
   g.kb_per_split = (kb_total + g.split_k - 1) / g.split_k;
   g.split_k = (kb_total + g.kb_per_split - 1) / g.kb_per_split;
-  g.b_resident = (!epi.atomic_f32 && kb_total <= NSTAGE && m_tiles > ctx->sm_count) ? 1 : 0;
+  g.b_resident = (!epi.atomic_f32 && kb_total <= gemm_stages(BN) && m_tiles > ctx->sm_count) ? 1 : 0;
   CUtensorMap ma, mb;
   int rc;
   if (mn_major) {
