@@ -100,7 +100,7 @@ int nt_raygen(nt_ctx* ctx, int64_t n, const int64_t* row, const int64_t* col, co
  *   gamma_point dev [total,3,20], gamma_dir dev [total,3,8] with feature (c, 2l+s) = sin / cos(fl(w_l * x_c)).
  * nt_network_forward: Network.forward nerf.py:101-124 on those encodings (flattened channel-major to [total,60] and
  *   [total,24], nerf.py:103-104), fp32 accuracy path.  rgb dev [total,3], sigma dev [total].  Workspace:
- *   nt_mlp_workspace_bytes(ctx, NT_PREC_FP32, total, 1, 0).  The fused NT_PREC_BF16 path never materialises the
+ *   nt_mlp_workspace_bytes(ctx, NT_PREC_FP32, total, 1, 0).  The fused tensor-core paths never materialise the
  *   encodings: use nt_mlp_forward for speed. */
 int nt_encode(nt_ctx* ctx, int64_t total, const float* points, const float* dirs, float* gamma_point, float* gamma_dir,
               void* stream);
@@ -132,7 +132,8 @@ int nt_shard_globals_resolve(nt_ctx* ctx, float* g4, void* stream);
 /* ---- encode + MLP: net_out nerf.py:200-219 = sample positions, Encoder.forward
  *      nerf.py:135-167, Network.forward nerf.py:101-124 -----------------------------------
  * t dev [N,P]; rays/dir_enc from nt_raygen; params dev flat fp32; packed dev = output of
- * nt_pack_weights (NT_PREC_BF16 only, else NULL).  rgb dev [N,P,3], sigma dev [N,P].
+ * nt_pack_weights WITH THE SAME PRECISION (every precision but NT_PREC_FP32, which takes NULL).  rgb dev [N,P,3],
+ * sigma dev [N,P].  NT_PREC_FP16 / TC32 / MIXED are rendering modes: train != 0 returns NT_ERR_UNSUPPORTED.
  * ws/ws_bytes: scratch of at least nt_mlp_workspace_bytes(); train != 0 keeps the activations
  * in `ws` for nt_mlp_backward. */
 size_t nt_mlp_workspace_bytes(nt_ctx* ctx, int precision, int64_t n, int p, int train);
