@@ -29,9 +29,9 @@ constexpr int OFF_W = 2 * ACT_BYTES;
 constexpr int OFF_BAR = OFF_W + N_STAGES * W_STAGE_BYTES;
 constexpr int OFF_WSIG = OFF_BAR + 128;  // w_sigma row, fp32 [256]
 constexpr int SMEM_BYTES = OFF_WSIG + 1024;
-constexpr int N_THREADS = 576;  // 16 epilogue warps + TMA producer + MMA issuer
-constexpr int WARP_TMA = 16, WARP_MMA = 17;
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = 2, BAR_ACC_FULL = 4, BAR_ACT_READY = 6, BAR_A_FULL = 8 };
+constexpr int N_THREADS = 640;  // 16 epilogue warps + TMA producer + MMA issuer + 2 column-sum warps (one per tile)
+constexpr int WARP_TMA = 16, WARP_MMA = 17, WARP_CS = 18;
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 2, BAR_ACC_FULL = 4, BAR_ACT_READY = 6, BAR_A_FULL = 8, BAR_CS_DONE = 10 };
 
 __host__ __device__ constexpr int step_chunks(int st) { return st == 0 ? 2 : 4; }
 constexpr int total_chunks() {
@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
       mbar_init(bar(BAR_ACC_FULL + tl), 1);
       mbar_init(bar(BAR_ACT_READY + tl), 2 * TILE_M);
       mbar_init(bar(BAR_A_FULL + tl), 1);
+      mbar_init(bar(BAR_CS_DONE + tl), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
                     }
                   }
                   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                  if (lit > 0) mbar_wait(bar(BAR_CS_DONE + tl), (lit - 1) & 1);  // column sums of that g_0 tile taken
                   mbar_expect_tx(bar(BAR_A_FULL + tl), 2 * CHUNK_A_BYTES);
                   tma_load_2d(act, &P.map_gu, 0, row0, bar(BAR_A_FULL + tl));
                   tma_load_2d(act + CHUNK_A_BYTES, &P.map_gu, 64, row0, bar(BAR_A_FULL + tl));
@@ -189,6 +191,46 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+  } else if (warp >= WARP_CS) {
+    // ===================== bias gradients: column sums of every step's gradient tile, straight from shared memory ==========
+    // db_l = sum over samples of g_l.  The epilogue used to reduce its fp32 values over the warp's 32 rows with 124 shuffles
+    // per thread and step (three quarters of its instructions); here one otherwise idle warp per tile reads the finished
+    // bf16 operand tile (the very values the weight-gradient GEMM multiplies) while the tensor core consumes it, and adds the
+    // 128 rows in fp32: lane = one 16-byte chunk (8 columns) of the 512-byte row, one atomic per column and tile.
+    const int tl = warp - WARP_CS;
+    const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
+    const uint32_t base = act + (lane >> 3) * CHUNK_A_BYTES;
+    const int j = lane & 7;
+    uint32_t it = 0;
+    mbar_wait(bar(BAR_ACT_READY + tl), 0);  // completion #0 is the epilogue warps' start-up arrive (no data behind it)
+    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
+      for (int st = 0; st < N_STEPS; ++st, ++it) {
+        mbar_wait(bar(BAR_ACT_READY + tl), (it + 1) & 1);  // completion #it+1: the output of step `it` is in place
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int r8 = 0; r8 < TILE_M / 8; ++r8) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(base + (r8 * 8 + r) * 128 + ((j ^ r) << 4)));
+            const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[2 * e] += __uint_as_float(w[e] << 16);
+              acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+            }
+          }
+        }
+        fence_proxy_async();  // these generic-proxy reads precede the next pair's TMA load into the same tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_CS_DONE + tl));  // the epilogue / the next pair's load may overwrite the tile
+        float* __restrict__ db = P.db[st] + lane * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(db + e, acc[e]);
+      }
+    }
   } else {
     // ===================== epilogue warps: per tile 4 lane quadrants x 2 column halves =====================
     const int tl = (warp >> 2) & 1;
@@ -215,7 +257,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
         const uint32_t mword[4] = {mw.x, mw.y, mw.z, mw.w};
         mbar_wait(bar(BAR_ACC_FULL + tl), it & 1);
         tc_fence_after();
-        float* __restrict__ db = P.db[st];
+        if (it > 0) mbar_wait(bar(BAR_CS_DONE + tl), (it - 1) & 1);  // the tile about to be overwritten has been column-summed
         uint32_t buf[2][32];
         tmem_ld32_issue(tmem_row + half * 128, buf[0]);
 #pragma unroll
@@ -247,18 +289,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
             st_shared_v4(dst + (x4 ^ (uint32_t)(((cb & 1) * 4 + qd) << 4)), pack_bf16(v[8 * qd], v[8 * qd + 1]),
                          pack_bf16(v[8 * qd + 2], v[8 * qd + 3]), pack_bf16(v[8 * qd + 4], v[8 * qd + 5]),
                          pack_bf16(v[8 * qd + 6], v[8 * qd + 7]));
-          // bias gradient: column sums over this warp's 32 rows (recursive halving), one atomic per column
-#pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int j = 0; j < o; ++j) {
-              const float send = up ? v[j] : v[j + o];
-              const float keep = up ? v[j + o] : v[j];
-              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-            }
-          }
-          atomicAdd(db + cb * 32 + lane, v[0]);
         }
         fence_proxy_async();
         tc_fence_before();

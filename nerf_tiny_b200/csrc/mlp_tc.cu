@@ -54,7 +54,6 @@ struct TcParams {
   uint32_t* st_bits;  // ReLU' bit masks of the 8 trunk layers, [8][S][8 words]: bit j of word cb = column cb*32+j > 0
 };
 
-__constant__ uint32_t c_tc_freq_point[10] = NT_FREQ_POINT_INIT;
 
 // PTX wrappers: tc_ptx.cuh (shared with bwd_tc.cu / gemm_tc.cu / mlp_tc32.cu)
 using namespace tcptx;
@@ -75,6 +74,27 @@ __device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
   r = fmaf(k, 1.7484555314695172e-07f, r);
   s = __sinf(r);
   c = __cosf(r);
+}
+
+// sin/cos feature pairs NP*G .. NP*G+NP-1 (pair index pi = c*10 + l, nerf.py:135-167) of one sample, packed to 16-bit.
+// G is a template parameter so that after unrolling every (c, l) is a compile-time constant: the frequencies become
+// immediates and the NP chains are independent straight-line code (with a run-time group index the compiler emitted one
+// branchy, serially dependent block per pair with spilled index tables: ~3 000 clk per tile instead of ~1 000)
+template <int NP, int G, bool F16>
+__device__ __forceinline__ void encode_group(const float (&pos)[3], uint32_t (&f)[NP]) {
+  constexpr uint32_t kFreq[10] = NT_FREQ_POINT_INIT;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int pi = G * NP + i;
+    if (pi < 30) {
+      const int c = pi / 10, l = pi % 10;
+      float sn, cs;
+      fast_sincos(__fmul_rn(__uint_as_float(kFreq[l]), pos[c]), sn, cs);
+      f[i] = F16 ? pack_f16(sn, cs) : pack_bf16(sn, cs);  // features (c*20+2l, c*20+2l+1)
+    } else {
+      f[i] = 0u;  // K padded 60 -> 64
+    }
+  }
 }
 
 enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_COLOUR = 3 };
@@ -364,19 +384,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
         pos[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.z, pc0), __fmul_rn(r1.w, pc1)), __fmul_rn(r2.x, pc2)), r3.y);
         pos[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.y, pc0), __fmul_rn(r2.z, pc1)), __fmul_rn(r2.w, pc2)), r3.z);
         uint32_t f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int pi = half * 16 + i;  // feature pair index = c*10 + l
-          if (pi < 30) {
-            const int c = pi / 10, l = pi % 10;
-            const float x = c == 0 ? pos[0] : (c == 1 ? pos[1] : pos[2]);
-            float sn, cs;
-            fast_sincos(__fmul_rn(__uint_as_float(c_tc_freq_point[l]), x), sn, cs);
-            f[i] = pack_bf16(sn, cs);  // features (c*20+2l, c*20+2l+1)
-          } else {
-            f[i] = 0u;  // K padded 60 -> 64
-          }
-        }
+        if (half == 0)
+          encode_group<16, 0, false>(pos, f);
+        else
+          encode_group<16, 1, false>(pos, f);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           st_shared_v4(sw.addr(enc, half * 4 + j), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -567,12 +578,13 @@ __device__ __forceinline__ void tmem2_dealloc_512(uint32_t taddr) {
 }
 
 // epilogue of one tile-layer for one thread: row `row` of the tile, column quarter `quarter`
-template <int KIND, bool F16>
+template <int KIND, bool F16, bool TL = false>
 __device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter, uint32_t tmem_row, uint32_t act,
                                            uint32_t bias_s, const float* __restrict__ aux_g, int quad_bar, const RowSwz sw,
                                            int64_t s, bool valid) {
   constexpr int NCB = KIND == EPI_COLOUR ? 1 : 2;  // 32-column blocks per quarter
   const int cb0 = quarter * NCB;
+  const int xf = TL ? P.dbg_layer - 100 : 0;  // timeline build only: experiment flags (1: no exchange, 2: no weight loads)
   float sig_acc = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
   uint32_t buf[2][32];
   tmem_ld32_issue(tmem_row + cb0 * 32, buf[0]);
@@ -595,7 +607,7 @@ __device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter
       const float4* __restrict__ ws = reinterpret_cast<const float4*>(aux_g + 7 * AUX_REC_FLOATS + AUX_EXTRA + cb * 32);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 w4 = __ldg(ws + j);
+        const float4 w4 = (TL && (xf & 2)) ? make_float4(0.5f, 0.25f, 0.125f, 1.f) : __ldg(ws + j);
         sig_acc = fmaf(fmaxf(v[4 * j + 0], 0.f), w4.x, sig_acc);
         sig_acc = fmaf(fmaxf(v[4 * j + 1], 0.f), w4.y, sig_acc);
         sig_acc = fmaf(fmaxf(v[4 * j + 2], 0.f), w4.z, sig_acc);
@@ -606,7 +618,10 @@ __device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter
       const float4* __restrict__ wc = reinterpret_cast<const float4*>(aux_g + 9 * AUX_REC_FLOATS + AUX_EXTRA + cb * 32);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 w0 = __ldg(wc + j), w1 = __ldg(wc + 32 + j), w2 = __ldg(wc + 64 + j);
+        const bool nw = TL && (xf & 2);
+        const float4 w0 = nw ? make_float4(0.5f, 0.25f, 0.125f, 1.f) : __ldg(wc + j);
+        const float4 w1 = nw ? make_float4(0.25f, 0.5f, 0.125f, 1.f) : __ldg(wc + 32 + j);
+        const float4 w2 = nw ? make_float4(0.125f, 0.25f, 0.5f, 1.f) : __ldg(wc + 64 + j);
         const float u0 = fmaxf(v[4 * j], 0.f), u1 = fmaxf(v[4 * j + 1], 0.f), u2 = fmaxf(v[4 * j + 2], 0.f),
                     u3 = fmaxf(v[4 * j + 3], 0.f);
         c0 = fmaf(u0, w0.x, fmaf(u1, w0.y, fmaf(u2, w0.z, fmaf(u3, w0.w, c0))));
@@ -630,19 +645,22 @@ __device__ __forceinline__ void epilogue_q(const TcParams& P, int L, int quarter
   // partial sums in accumulator columns they have already drained, quarter 0 adds them up after a 128-thread barrier
   if (KIND == EPI_RELU_SIGMA || KIND == EPI_COLOUR) {
     constexpr int QW = KIND == EPI_COLOUR ? 32 : 64;  // columns per quarter
-    if (quarter != 0) tmem_st4(tmem_row + quarter * QW, sig_acc, c0, c1, c2);
-    tc_fence_before();
-    asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
-    tc_fence_after();
+    const bool nx = TL && (xf & 1);
+    if (quarter != 0 && !nx) tmem_st4(tmem_row + quarter * QW, sig_acc, c0, c1, c2);
+    if (!nx) {
+      tc_fence_before();
+      asm volatile("bar.sync %0, 128;" ::"r"(quad_bar) : "memory");
+      tc_fence_after();
+    }
     if (quarter == 0) {
+      float o[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (!nx) tmem_ld4x3(tmem_row + QW, tmem_row + 2 * QW, tmem_row + 3 * QW, o);
 #pragma unroll
-      for (int q = 1; q < 4; ++q) {
-        float o_s, o0, o1, o2;
-        tmem_ld4(tmem_row + q * QW, o_s, o0, o1, o2);
-        sig_acc += o_s;
-        c0 += o0;
-        c1 += o1;
-        c2 += o2;
+      for (int q = 0; q < 3; ++q) {  // same order of additions as before
+        sig_acc += o[4 * q];
+        c0 += o[4 * q + 1];
+        c1 += o[4 * q + 2];
+        c2 += o[4 * q + 3];
       }
       if (KIND == EPI_RELU_SIGMA) {
         const float z = sig_acc + __ldg(aux_g + 7 * AUX_REC_FLOATS + AUX_SIG_B);
@@ -864,18 +882,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
         pos[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.z, pc0), __fmul_rn(r1.w, pc1)), __fmul_rn(r2.x, pc2)), r3.y);
         pos[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.y, pc0), __fmul_rn(r2.z, pc1)), __fmul_rn(r2.w, pc2)), r3.z);
         uint32_t f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int pi = quarter * 8 + i;  // feature pair index = c*10 + l
-          if (pi < 30) {
-            const int c = pi / 10, l = pi % 10;
-            const float x = c == 0 ? pos[0] : (c == 1 ? pos[1] : pos[2]);
-            float sn, cs;
-            fast_sincos(__fmul_rn(__uint_as_float(c_tc_freq_point[l]), x), sn, cs);
-            f[i] = pack16<F16>(sn, cs);
-          } else {
-            f[i] = 0u;  // K padded 60 -> 64
-          }
+        switch (quarter) {  // warp-uniform
+          case 0: encode_group<8, 0, F16>(pos, f); break;
+          case 1: encode_group<8, 1, F16>(pos, f); break;
+          case 2: encode_group<8, 2, F16>(pos, f); break;
+          default: encode_group<8, 3, F16>(pos, f); break;
         }
         const uint32_t enc = sbase + OFF_ENC + tl * CHUNK_A_BYTES;
         st_shared_v4(sw.addr(enc, quarter * 2), f[0], f[1], f[2], f[3]);
@@ -899,13 +910,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
           if (TL && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
             reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 4 + tl * 2] = clock64();
           if (L == 7)
-            epilogue_q<EPI_RELU_SIGMA, F16>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+            epilogue_q<EPI_RELU_SIGMA, F16, TL>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
           else if (L == 8)
-            epilogue_q<EPI_LINEAR, F16>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+            epilogue_q<EPI_LINEAR, F16, TL>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
           else if (L == 9)
-            epilogue_q<EPI_COLOUR, F16>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+            epilogue_q<EPI_COLOUR, F16, TL>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
           else
-            epilogue_q<EPI_RELU, F16>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
+            epilogue_q<EPI_RELU, F16, TL>(P, L, quarter, tmem_row, act, bias_s, aux_g, quad_bar, sw, s_t[tl], valid_t[tl]);
           if (L == 4) {
             // the xyz features of this tile are dead (all its MMAs retired): store the view features in their place
             if (quarter == 0) {
@@ -929,6 +940,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bar(B_ACT_READY + tl));
+          }
+          // Pull the lines that later epilogues read with plain loads into L1 a layer or more ahead (each of them was an
+          // exposed L2 round trip of 800-2500 clk in the clock64 timeline): the view features, the head weights, and the
+          // next pair's t / ray records.
+          if (L == 2) {
+            prefetch_l1(P.dir_enc + ray_t[tl] * 24);
+            prefetch_l1(P.dir_enc + ray_t[tl] * 24 + 23);
+          } else if (L == 5 && tl == 1 && lane < 2) {
+            prefetch_l1(aux_g + 7 * AUX_REC_FLOATS + AUX_EXTRA + quarter * 64 + lane * 32);
+          } else if (L == 7 && tl == 1 && lane < 3) {
+            prefetch_l1(aux_g + 9 * AUX_REC_FLOATS + AUX_EXTRA + lane * 128 + quarter * 32);
+          } else if (L == 8 && itp + 1 < iters) {
+            const int64_t sn = ((int64_t)(pair + (int)gridDim.x) * 2 + tl) * TILE_M + row;
+            if (sn < P.total) {
+              if ((lane & 31) == 0 && quarter == 0) prefetch_l1(P.t + sn);
+              if (quarter == 1) prefetch_l1(P.rays + (P.p_shift >= 0 ? (sn >> P.p_shift) : sn / P.p) * 16);
+            }
           }
           if (TL && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
             reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 5 + tl * 2] = clock64();

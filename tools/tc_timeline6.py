@@ -13,7 +13,7 @@ packed = ctx.pack(flat, 2)
 rays, _, de = ctx.raygen(row.to(dev), col.to(dev), pb.float().to(dev), synth.k_inv_of(400, 400, synth.focal_of(400)).to(dev))
 t = (torch.rand(n, 128, device=dev) * 4 + 2)
 for _ in range(2):
-    rgb, sig, dbg = ctx.mlp_forward_debug(t, rays, de, flat, packed, 100)
+    rgb, sig, dbg = ctx.mlp_forward_debug(t, rays, de, flat, packed, 100 + int(os.environ.get("NT_TL_FLAGS", "0")))
 torch.cuda.synchronize()
 prof = dbg.cpu().numpy().view(np.int64).reshape(-1)[:4 * 10 * 16].reshape(4, 10, 16)
 t0 = prof[1, 0, 0]
