@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnerftiny.so")
+LIB_PATH = os.environ.get("NT_LIB_PATH") or os.path.join(HERE, "libnerftiny.so")  # NT_LIB_PATH: A/B builds (tools/)
 
 NT_OK = 0
 NT_ERR_RANGE = -3

@@ -22,16 +22,16 @@ constexpr int TILE_M = 128;
 constexpr int CHUNK_A_BYTES = TILE_M * 128;
 constexpr int ACT_BYTES = 4 * CHUNK_A_BYTES;
 constexpr int W_STAGE_BYTES = 256 * 128;
-constexpr int N_STAGES = 2;
+constexpr int N_STAGES = 3;  // 3 x 32 KB: without the forward kernel's feature tiles there is room for a third slot
 constexpr int N_STEPS = 9;
 constexpr int OFF_ACT = 0;
 constexpr int OFF_W = 2 * ACT_BYTES;
 constexpr int OFF_BAR = OFF_W + N_STAGES * W_STAGE_BYTES;
-constexpr int OFF_WSIG = OFF_BAR + 128;  // w_sigma row, fp32 [256]
+constexpr int OFF_WSIG = OFF_BAR + 256;  // w_sigma row, fp32 [256]
 constexpr int SMEM_BYTES = OFF_WSIG + 1024;
 constexpr int N_THREADS = 640;  // 16 epilogue warps + TMA producer + MMA issuer + 2 column-sum warps (one per tile)
 constexpr int WARP_TMA = 16, WARP_MMA = 17, WARP_CS = 18;
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = 2, BAR_ACC_FULL = 4, BAR_ACT_READY = 6, BAR_A_FULL = 8, BAR_CS_DONE = 10 };
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_ACC_FULL = 6, BAR_ACT_READY = 8, BAR_A_FULL = 10, BAR_CS_DONE = 12 };
 
 __host__ __device__ constexpr int step_chunks(int st) { return st == 0 ? 2 : 4; }
 constexpr int total_chunks() {
@@ -51,10 +51,16 @@ struct BwdParams {
   float* db[N_STEPS];             // bias gradients: point_info, layer 7 .. layer 0
   int64_t total;
   int num_pairs;
+  long long* prof;                // optional clock64 timeline of block 0's first pairs (tools/chain_timeline.py)
 };
 
 // PTX wrappers: tc_ptx.cuh
 using namespace tcptx;
+// diagnostic timeline: prof[(pair_local * 9 + step) * 16 + slot], block 0, first 4 pairs
+#define BW_PROF(pl_, st_, slot_)                                                          \
+  do {                                                                                    \
+    if (P.prof && blockIdx.x == 0 && (pl_) < 4) P.prof[((pl_) * 9 + (st_)) * 16 + (slot_)] = clock64(); \
+  } while (0)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) { return desc_kmajor(saddr); }
 __host__ __device__ constexpr uint32_t umma_idesc(int n) { return idesc_f16kind(TILE_M, n, true); }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -67,12 +73,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 96);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 128);
 
   if (threadIdx.x == 0) {
     if (sbase & 1023) __trap();
     for (int s = 0; s < N_STAGES; ++s) {
-      mbar_init(bar(BAR_W_FULL + s), 1);
+      mbar_init(bar(BAR_W_FULL + s), 32);  // one cp.async-completion arrive per producer lane
       mbar_init(bar(BAR_W_EMPTY + s), 1);
     }
     for (int tl = 0; tl < 2; ++tl) {
@@ -96,53 +102,57 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
 
   if (warp == WARP_TMA) {
     // ===================== weight producer =====================
-    if (lane == 0) {
-      uint32_t q = 0;
-      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
-        const uint8_t* src = P.packed;
-        for (int st = 0; st < N_STEPS; ++st)
-          for (int kc = 0; kc < step_chunks(st); ++kc, ++q) {
-            const uint32_t stage = q & 1;
-            mbar_wait(bar(BAR_W_EMPTY + stage), ((q >> 1) & 1) ^ 1);
-            mbar_expect_tx(bar(BAR_W_FULL + stage), W_STAGE_BYTES);
-            tma_bulk_g2s(sbase + OFF_W + stage * W_STAGE_BYTES, src, W_STAGE_BYTES, bar(BAR_W_FULL + stage));
-            src += W_STAGE_BYTES;
-          }
-      }
+    // The whole warp copies each 32 KB chunk with 16-byte cp.async (LDGSTS) instead of one TMA bulk copy: the TMA unit of
+    // this SM is busy draining 128 KB of gradient-tile stores per step, and a bulk load queued behind them arrived 2 000 to
+    // 8 500 clk after it was issued (clock64 timeline) - the tensor core waited for weights in every step.  cp.async takes the
+    // LSU path, so weight loads and stash stores no longer share a queue.
+    uint32_t q = 0;
+    int pl = 0;
+    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pl) {
+      const uint8_t* src = P.packed + lane * 16;
+      for (int st = 0; st < N_STEPS; ++st)
+        for (int kc = 0; kc < step_chunks(st); ++kc, ++q) {
+          const uint32_t stage = q % N_STAGES;
+          mbar_wait(bar(BAR_W_EMPTY + stage), ((q / N_STAGES) & 1) ^ 1);
+          if (lane == 0 && kc == 1) BW_PROF(pl, st, 8);
+          if (lane == 0 && kc == 3) BW_PROF(pl, st, 9);
+          const uint32_t dst = sbase + OFF_W + stage * W_STAGE_BYTES + lane * 16;
+#pragma unroll 16
+          for (int i = 0; i < W_STAGE_BYTES / 512; ++i)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(src + i * 512) : "memory");
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar(BAR_W_FULL + stage)) : "memory");
+          src += W_STAGE_BYTES;
+        }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == WARP_MMA) {
-    // ===================== MMA issuer (+ operand loads / gradient stash by TMA) =====================
+    // ===================== MMA issuer (+ the g_u operand loads) =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(256);
       uint32_t q = 0, lit = 0, pl = 0;
-      int prev_pair = -1;
       for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pl) {
         for (int st = 0; st < N_STEPS; ++st, ++lit) {
           const int nch = step_chunks(st);
           for (int kc = 0; kc < nch; ++kc, ++q) {
-            const uint32_t stage = q & 1;
-            mbar_wait(bar(BAR_W_FULL + stage), (q >> 1) & 1);
+            const uint32_t stage = q % N_STAGES;
+            mbar_wait(bar(BAR_W_FULL + stage), (q / N_STAGES) & 1);
+            fence_proxy_async();  // the chunk was written through the generic proxy (cp.async), the tensor core reads it async
             tc_fence_after();
             const uint32_t b_addr = sbase + OFF_W + stage * W_STAGE_BYTES;
+            BW_PROF(pl, st, 2 + kc);
 #pragma unroll
             for (int tl = 0; tl < 2; ++tl) {
               const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
               if (kc == 0) {
                 mbar_wait(bar(BAR_ACT_READY + tl), lit & 1);  // epilogue done: operand in place, accumulator drained
                 tc_fence_after();
-                const int row0 = (pair * 2 + tl) * TILE_M;
+                BW_PROF(pl, st, tl);
                 if (st == 0) {
-                  // stash the previous pair's last gradient tile (g_0), then fetch this pair's g_u tile
-                  if (prev_pair >= 0) {
-                    const int prow0 = (prev_pair * 2 + tl) * TILE_M;
-                    if (prow0 < P.total) {
-#pragma unroll
-                      for (int c = 0; c < 4; ++c) tma_store_2d(&P.map_out[N_STEPS - 1], c * 64, prow0, act + c * CHUNK_A_BYTES);
-                      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                  }
-                  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                  if (lit > 0) mbar_wait(bar(BAR_CS_DONE + tl), (lit - 1) & 1);  // column sums of that g_0 tile taken
+                  // fetch this pair's g_u tile over the previous pair's g_0 tile: its stash stores have left shared memory
+                  // (the epilogue's storing threads wait for that before the arrive of the last step) and its column sums
+                  // have been taken
+                  const int row0 = (pair * 2 + tl) * TILE_M;
+                  if (lit > 0) mbar_wait(bar(BAR_CS_DONE + tl), (lit - 1) & 1);
                   mbar_expect_tx(bar(BAR_A_FULL + tl), 2 * CHUNK_A_BYTES);
                   tma_load_2d(act, &P.map_gu, 0, row0, bar(BAR_A_FULL + tl));
                   tma_load_2d(act + CHUNK_A_BYTES, &P.map_gu, 64, row0, bar(BAR_A_FULL + tl));
@@ -154,42 +164,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 umma_bf16(d_tmem, umma_desc(a_addr + j * 32), umma_desc(b_addr + j * 32), idesc, (kc | j) != 0);
-              if (st > 0) {
-                // the operand of this step is the output of step st-1: stash it for the weight-gradient GEMM, one 16 KB
-                // box per K-chunk step so the next chunks' weight loads are not queued behind 128 KB of stores
-                const int row0 = (pair * 2 + tl) * TILE_M;
-                if (row0 < P.total) {
-                  tma_store_2d(&P.map_out[st - 1], kc * 64, row0, a_addr);
-                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-              }
               if (kc == nch - 1) {
-                // Issuing these stores from an elected epilogue thread instead (so that this thread never waits on the TMA unit)
-                // was measured SLOWER: 428-447 vs 395 us per 1024-ray step - the cost of the stash is contention in the
-                // memory system (342 us with no stores at all), not this wait.
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // epilogue will overwrite the operand tile
                 umma_commit(bar(BAR_ACC_FULL + tl));
+                BW_PROF(pl, st, 6 + tl);
               }
             }
             umma_commit(bar(BAR_W_EMPTY + stage));
           }
         }
-        prev_pair = pair;
       }
-      // the last pair's g_0 tiles
-      if (prev_pair >= 0) {
-        for (int tl = 0; tl < 2; ++tl) {
-          mbar_wait(bar(BAR_ACT_READY + tl), lit & 1);
-          const int prow0 = (prev_pair * 2 + tl) * TILE_M;
-          if (prow0 < P.total) {
-            const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tma_store_2d(&P.map_out[N_STEPS - 1], c * 64, prow0, act + c * CHUNK_A_BYTES);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        }
-      }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp >= WARP_CS) {
     // ===================== bias gradients: column sums of every step's gradient tile, straight from shared memory ==========
@@ -226,6 +209,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
         fence_proxy_async();  // these generic-proxy reads precede the next pair's TMA load into the same tile
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BAR_CS_DONE + tl));  // the epilogue / the next pair's load may overwrite the tile
+        if (lane == 0) BW_PROF((int)(it / N_STEPS), st, 14 + tl);
         float* __restrict__ db = P.db[st] + lane * 8;
 #pragma unroll
         for (int e = 0; e < 8; ++e) atomicAdd(db + e, acc[e]);
@@ -233,6 +217,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
     }
   } else {
     // ===================== epilogue warps: per tile 4 lane quadrants x 2 column halves =====================
+    // Every step's gradient tile is also the weight-gradient GEMM's operand: the 128 threads of a (tile, column half) group
+    // hand each 64-column chunk to the TMA unit as soon as they have written it (one 16 KB tensor store per chunk, issued by
+    // the group's elected thread after a 128-thread named barrier), so the stores drain to HBM during the rest of the
+    // epilogue AND the next step's MMAs instead of holding the MMA thread before its commit (2 800 of 10 300 clk per step
+    // in the clock64 timeline when the MMA thread issued and awaited them).
     const int tl = (warp >> 2) & 1;
     const int half = warp >> 3;
     const int row = (warp & 3) * 32 + lane;
@@ -240,10 +229,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + tl * 256;
     const uint32_t row_off = row * 128, x4 = (row & 7) << 4;
     const uint32_t wsig_s = sbase + OFF_WSIG;
+    const int grp_bar = 1 + tl * 2 + half;                 // named barrier of this (tile, half) group
+    const bool storer = (warp & 3) == 0 && lane == 0;      // the group's elected thread
     uint32_t it = 0;
+    int pl = 0;
+    const bool stamper = (warp & 3) == 0 && half == 0 && lane == 0;
     mbar_arrive(bar(BAR_ACT_READY + tl));  // nothing to protect before the first pair
-    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
-      const int64_t s = ((int64_t)pair * 2 + tl) * TILE_M + row;
+    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pl) {
+      const int row0 = (pair * 2 + tl) * TILE_M;
+      const int64_t s = (int64_t)row0 + row;
       const bool valid = s < P.total;
       const float gz = valid ? __ldg(P.gzsig + s) : 0.f;
       for (int st = 0; st < N_STEPS; ++st, ++it) {
@@ -258,6 +252,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
         mbar_wait(bar(BAR_ACC_FULL + tl), it & 1);
         tc_fence_after();
         if (it > 0) mbar_wait(bar(BAR_CS_DONE + tl), (it - 1) & 1);  // the tile about to be overwritten has been column-summed
+        // ... and the previous step's stash stores of this group's two chunks have finished reading it (normally long ago)
+        if (storer) tma_store_wait_read0();
+        asm volatile("bar.sync %0, 128;" ::"r"(grp_bar) : "memory");
+        if (stamper) BW_PROF(pl, st, 10 + tl);
         uint32_t buf[2][32];
         tmem_ld32_issue(tmem_row + half * 128, buf[0]);
 #pragma unroll
@@ -289,12 +287,26 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
             st_shared_v4(dst + (x4 ^ (uint32_t)(((cb & 1) * 4 + qd) << 4)), pack_bf16(v[8 * qd], v[8 * qd + 1]),
                          pack_bf16(v[8 * qd + 2], v[8 * qd + 3]), pack_bf16(v[8 * qd + 4], v[8 * qd + 5]),
                          pack_bf16(v[8 * qd + 6], v[8 * qd + 7]));
+          if (i & 1) {
+            // K-chunk half*2 + i/2 of the new tile is complete: make it visible to the async proxy and stash it
+            fence_proxy_async();
+            asm volatile("bar.sync %0, 128;" ::"r"(grp_bar) : "memory");
+            if (storer && row0 < P.total) {
+              const int kc = half * 2 + (i >> 1);
+              tma_store_2d(&P.map_out[st], kc * 64, row0, act + kc * CHUNK_A_BYTES);
+              tma_store_commit();
+            }
+          }
         }
-        fence_proxy_async();
+        // the next pair's g_u load overwrites chunks 0-1 of this tile right after the arrive of the LAST step
+        if (st == N_STEPS - 1 && storer) tma_store_wait_read0();
+        if (st == N_STEPS - 1) asm volatile("bar.sync %0, 128;" ::"r"(grp_bar) : "memory");
         tc_fence_before();
         mbar_arrive(bar(BAR_ACT_READY + tl));
+        if (stamper) BW_PROF(pl, st, 12 + tl);
       }
     }
+    if (storer) tma_store_wait0();
   }
 
   __syncwarp();
@@ -351,6 +363,10 @@ __global__ void pack_bwd_kernel(const float* __restrict__ params, uint8_t* __res
 
 size_t nt_bwd_tc_packed_bytes() { return PACKED_BWD_BYTES; }
 
+static long long* g_chain_prof = nullptr;
+// diagnostics only (tools/chain_timeline.py): device buffer of 4 * 9 * 16 int64 that the next chain launches stamp
+extern "C" void nt_debug_set_chain_prof(void* p) { g_chain_prof = (long long*)p; }
+
 int nt_bwd_tc_pack(nt_ctx* ctx, const float* params, void* packed, cudaStream_t st) {
   const LayerTable T = nt_layers();
   PackBwdArgs a;
@@ -387,6 +403,7 @@ int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9]
   P.gzsig = gzsig;
   P.wsig = wsig;
   P.total = S;
+  P.prof = g_chain_prof;
   const int64_t tiles = (S + TILE_M - 1) / TILE_M;
   P.num_pairs = (int)((tiles + 1) / 2);
   int grid = ctx->sm_count < P.num_pairs ? ctx->sm_count : P.num_pairs;

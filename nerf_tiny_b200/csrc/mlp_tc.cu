@@ -721,7 +721,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
           for (int li = 0; li < nl; ++li, ++q) {
             const int kc = load_chunk(L, li);
             const uint32_t stage = q % NST;
-            mbar_wait(bar(B_W_EMPTY + stage), ((q / NST) & 1) ^ 1);
+            // polled: for the peer CTA the leader's multicast commit is a remote arrive, which does not wake a thread that is
+            // suspended inside try_wait (it would sleep out the ~700 clk time limit before reloading the slot)
+            mbar_spin(bar(B_W_EMPTY + stage), ((q / NST) & 1) ^ 1);
             mbar_expect_tx(bar(B_W_FULL + stage), hbytes);
             tma_bulk_g2s(sbase + OFF_W + stage * HALF_STAGE, src + kc * bytes + crank * hbytes, hbytes,
                          bar(B_W_FULL + stage));
@@ -940,23 +942,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_tc
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bar(B_ACT_READY + tl));
-          }
-          // Pull the lines that later epilogues read with plain loads into L1 a layer or more ahead (each of them was an
-          // exposed L2 round trip of 800-2500 clk in the clock64 timeline): the view features, the head weights, and the
-          // next pair's t / ray records.
-          if (L == 2) {
-            prefetch_l1(P.dir_enc + ray_t[tl] * 24);
-            prefetch_l1(P.dir_enc + ray_t[tl] * 24 + 23);
-          } else if (L == 5 && tl == 1 && lane < 2) {
-            prefetch_l1(aux_g + 7 * AUX_REC_FLOATS + AUX_EXTRA + quarter * 64 + lane * 32);
-          } else if (L == 7 && tl == 1 && lane < 3) {
-            prefetch_l1(aux_g + 9 * AUX_REC_FLOATS + AUX_EXTRA + lane * 128 + quarter * 32);
-          } else if (L == 8 && itp + 1 < iters) {
-            const int64_t sn = ((int64_t)(pair + (int)gridDim.x) * 2 + tl) * TILE_M + row;
-            if (sn < P.total) {
-              if ((lane & 31) == 0 && quarter == 0) prefetch_l1(P.t + sn);
-              if (quarter == 1) prefetch_l1(P.rays + (P.p_shift >= 0 ? (sn >> P.p_shift) : sn / P.p) * 16);
-            }
           }
           if (TL && blockIdx.x == 0 && itp < 4 && threadIdx.x == 0)
             reinterpret_cast<long long*>(P.dbg)[(itp * 10 + L) * 16 + 5 + tl * 2] = clock64();
