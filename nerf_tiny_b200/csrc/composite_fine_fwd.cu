@@ -141,43 +141,10 @@ __device__ __forceinline__ void load_lane(int64_t ray, int lane, int nc, int nf,
   }
 }
 
-template <bool PERM>
-__global__ void __launch_bounds__(128) composite_fine_fwd_kernel(int64_t n, int nc, int nf, const float* __restrict__ t_c,
-                                                                 const float* __restrict__ rgb_c,
-                                                                 const float* __restrict__ sigma_c,
-                                                                 const float* __restrict__ t_f,
-                                                                 const float* __restrict__ rgb_f,
-                                                                 const float* __restrict__ sigma_f, float last,
-                                                                 float* __restrict__ c_out, float* __restrict__ weights,
-                                                                 uint8_t* __restrict__ perm) {
-  const int lane = threadIdx.x & 31;
-  const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (ray >= n) return;
-  const int tot = nc + nf;
+// compositing over the sorted channels of one ray (one warp): delta = diff(t) ++ [last] (nerf.py:315), inclusive fp64 prefix
+__device__ __forceinline__ void composite_sorted(const float (&ch)[5][8], int64_t ray, int lane, int tot, float last,
+                                                 float* __restrict__ c_out, float* __restrict__ weights) {
   const bool live = lane * 8 < tot;
-  float ch[5][8];
-  load_lane(ray, lane, nc, nf, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, ch);
-  if (PERM) {
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-      unsigned long long kv[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) kv[r] = ((unsigned long long)f2ord(ch[c][r]) << 32) | (unsigned)(lane * 8 + r);
-      warp_sort_256_call(kv, lane);
-      uint32_t lo = 0, hi = 0;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        ch[c][r] = ord2f((uint32_t)(kv[r] >> 32));
-        const uint32_t id = (uint32_t)kv[r] & 0xffu;
-        if (r < 4) lo |= id << (8 * r); else hi |= id << (8 * (r - 4));
-      }
-      if (live) *reinterpret_cast<uint2*>(perm + (ray * 5 + c) * tot + lane * 8) = make_uint2(lo, hi);
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 5; ++c) warp_sort_256<float>(ch[c], lane);
-  }
-  // ---- compositing over the sorted channels: delta = diff(t) ++ [last] (nerf.py:315), inclusive fp64 prefix ----
   const float t_next_lane = __shfl_down_sync(FULL, ch[0][0], 1);
   float a[8], dl[8];
   double run = 0.0, pre[8];
@@ -217,6 +184,105 @@ __global__ void __launch_bounds__(128) composite_fine_fwd_kernel(int64_t n, int 
   }
 }
 
+template <bool PERM>
+__global__ void __launch_bounds__(128) composite_fine_fwd_kernel(int64_t n, int nc, int nf, const float* __restrict__ t_c,
+                                                                 const float* __restrict__ rgb_c,
+                                                                 const float* __restrict__ sigma_c,
+                                                                 const float* __restrict__ t_f,
+                                                                 const float* __restrict__ rgb_f,
+                                                                 const float* __restrict__ sigma_f, float last,
+                                                                 float* __restrict__ c_out, float* __restrict__ weights,
+                                                                 uint8_t* __restrict__ perm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ray >= n) return;
+  const int tot = nc + nf;
+  const bool live = lane * 8 < tot;
+  float ch[5][8];
+  load_lane(ray, lane, nc, nf, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, ch);
+  (void)live;
+  if (PERM) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      unsigned long long kv[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) kv[r] = ((unsigned long long)f2ord(ch[c][r]) << 32) | (unsigned)(lane * 8 + r);
+      warp_sort_256_call(kv, lane);
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        ch[c][r] = ord2f((uint32_t)(kv[r] >> 32));
+        const uint32_t id = (uint32_t)kv[r] & 0xffu;
+        if (r < 4) lo |= id << (8 * r); else hi |= id << (8 * (r - 4));
+      }
+      if (live) *reinterpret_cast<uint2*>(perm + (ray * 5 + c) * tot + lane * 8) = make_uint2(lo, hi);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) warp_sort_256<float>(ch[c], lane);
+  }
+  composite_sorted(ch, ray, lane, tot, last, c_out, weights);
+}
+
+// Training variant: FIVE warps per ray, one per channel.  The (key, index) sorts that produce the permutations are five
+// independent serial shuffle chains; on one warp they made the launch latency-bound (45 us for ANY batch up to ~2 000 rays,
+// 7 warps per SM at the 1024-ray training batch).  Each warp sorts its own channel, parks the sorted values in shared
+// memory, and warp 0 composites.
+__global__ void __launch_bounds__(160) composite_fine_fwd5_kernel(int64_t n, int nc, int nf, const float* __restrict__ t_c,
+                                                                  const float* __restrict__ rgb_c,
+                                                                  const float* __restrict__ sigma_c,
+                                                                  const float* __restrict__ t_f,
+                                                                  const float* __restrict__ rgb_f,
+                                                                  const float* __restrict__ sigma_f, float last,
+                                                                  float* __restrict__ c_out, float* __restrict__ weights,
+                                                                  uint8_t* __restrict__ perm) {
+  __shared__ float s_ch[5][256];
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+  const int64_t ray = blockIdx.x;
+  const int tot = nc + nf;
+  const bool live = lane * 8 < tot;
+  float v[8];
+  if (!live) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = __int_as_float(0x7f800000);
+  } else {
+    const bool co = lane * 8 < nc;
+    const int64_t s0 = co ? ray * nc + lane * 8 : ray * nf + (lane * 8 - nc);
+    if (c == 0 || c == 4) {
+      const float4* p = reinterpret_cast<const float4*>((c == 0 ? (co ? t_c : t_f) : (co ? sigma_c : sigma_f)) + s0);
+      const float4 x0 = __ldg(p), x1 = __ldg(p + 1);
+      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+      v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+    } else {
+      const float* p = (co ? rgb_c : rgb_f) + s0 * 3 + (c - 1);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = __ldg(p + 3 * r);
+    }
+  }
+  unsigned long long kv[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) kv[r] = ((unsigned long long)f2ord(v[r]) << 32) | (unsigned)(lane * 8 + r);
+  warp_sort_256<unsigned long long>(kv, lane);
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    s_ch[c][lane * 8 + r] = ord2f((uint32_t)(kv[r] >> 32));
+    const uint32_t id = (uint32_t)kv[r] & 0xffu;
+    if (r < 4) lo |= id << (8 * r); else hi |= id << (8 * (r - 4));
+  }
+  if (live) *reinterpret_cast<uint2*>(perm + (ray * 5 + c) * tot + lane * 8) = make_uint2(lo, hi);
+  __syncthreads();
+  if (c != 0) return;
+  float ch[5][8];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const float4 x0 = *reinterpret_cast<const float4*>(&s_ch[k][lane * 8]), x1 = *reinterpret_cast<const float4*>(&s_ch[k][lane * 8 + 4]);
+    ch[k][0] = x0.x; ch[k][1] = x0.y; ch[k][2] = x0.z; ch[k][3] = x0.w;
+    ch[k][4] = x1.x; ch[k][5] = x1.y; ch[k][6] = x1.z; ch[k][7] = x1.w;
+  }
+  composite_sorted(ch, ray, lane, tot, last, c_out, weights);
+}
+
 }  // namespace
 
 int nt_launch_composite_fine_fwd(nt_ctx* ctx, int64_t n, const float* t_c, const float* rgb_c, const float* sigma_c,
@@ -224,7 +290,7 @@ int nt_launch_composite_fine_fwd(nt_ctx* ctx, int64_t n, const float* t_c, const
                                  float* weights, uint8_t* perm, cudaStream_t st) {
   const unsigned blocks = (unsigned)((n + 3) / 4);
   if (perm)
-    composite_fine_fwd_kernel<true><<<blocks, 128, 0, st>>>(n, ctx->n_coarse, ctx->n_fine, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, last, c_out,
+    composite_fine_fwd5_kernel<<<(unsigned)n, 160, 0, st>>>(n, ctx->n_coarse, ctx->n_fine, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, last, c_out,
                                                             weights, perm);
   else
     composite_fine_fwd_kernel<false><<<blocks, 128, 0, st>>>(n, ctx->n_coarse, ctx->n_fine, t_c, rgb_c, sigma_c, t_f, rgb_f, sigma_f, last, c_out,
