@@ -49,7 +49,6 @@ struct Tc32Params {
   int num_tiles;
 };
 
-__constant__ uint32_t c_freq32[10] = NT_FREQ_POINT_INIT;
 
 // x (two values) -> packed fp16 hi pair and packed fp16 scaled-residual pair
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
@@ -59,6 +58,26 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
 }
 
 enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_COLOUR = 3 };
+
+// feature pairs 8*G .. 8*G+7 (pair index pi = c*10 + l) of one sample, accurate sincosf, split into hi / lo fp16 parts.  G is
+// a template parameter so that every (c, l) is a compile-time constant after unrolling: straight-line independent chains
+// instead of one branchy, serially dependent block per pair with run-time table look-ups (as in mlp_tc.cu::encode_group)
+template <int G>
+__device__ __forceinline__ void encode_group32(const float (&pos)[3], uint32_t (&fh)[8], uint32_t (&fl)[8]) {
+  constexpr uint32_t kFreq[10] = NT_FREQ_POINT_INIT;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int pi = G * 8 + i;
+    if (pi < 30) {
+      const int c = pi / 10, l = pi % 10;
+      float sn, cs;
+      sincosf(__fmul_rn(__uint_as_float(kFreq[l]), pos[c]), &sn, &cs);
+      split2(sn, cs, fh[i], fl[i]);  // features (c*20+2l, c*20+2l+1)
+    } else {
+      fh[i] = fl[i] = 0u;  // K padded 60 -> 64
+    }
+  }
+}
 
 // epilogue of one layer for one thread: row `row` of the tile (= one TMEM lane), column quarter `quarter`
 template <int KIND>
@@ -267,18 +286,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc32_kernel(const __grid_con
         pos[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.z, pc0), __fmul_rn(r1.w, pc1)), __fmul_rn(r2.x, pc2)), r3.y);
         pos[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.y, pc0), __fmul_rn(r2.z, pc1)), __fmul_rn(r2.w, pc2)), r3.z);
         uint32_t fh[8], fl[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int pi = quarter * 8 + i;  // feature pair index = c*10 + l
-          if (pi < 30) {
-            const int c = pi / 10, l = pi % 10;
-            const float x = c == 0 ? pos[0] : (c == 1 ? pos[1] : pos[2]);
-            float sn, cs;
-            sincosf(__fmul_rn(__uint_as_float(c_freq32[l]), x), &sn, &cs);
-            split2(sn, cs, fh[i], fl[i]);  // features (c*20+2l, c*20+2l+1)
-          } else {
-            fh[i] = fl[i] = 0u;  // K padded 60 -> 64
-          }
+        switch (quarter) {  // warp-uniform; the group index must be a compile-time constant (see encode_group32)
+          case 0: encode_group32<0>(pos, fh, fl); break;
+          case 1: encode_group32<1>(pos, fh, fl); break;
+          case 2: encode_group32<2>(pos, fh, fl); break;
+          default: encode_group32<3>(pos, fh, fl); break;
         }
         st_shared_v4(sw.addr(enc_hi, quarter * 2), fh[0], fh[1], fh[2], fh[3]);
         st_shared_v4(sw.addr(enc_hi, quarter * 2 + 1), fh[4], fh[5], fh[6], fh[7]);

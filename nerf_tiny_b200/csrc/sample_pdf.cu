@@ -74,35 +74,73 @@ __device__ __forceinline__ int count_less(const float* cdf, float u) {
   return lo;
 }
 
+// Forward.  Each lane owns nf/32 CONSECUTIVE outputs k: u is non-decreasing in k, so the lane needs ONE 7-step binary search
+// (for its last u); the counts of its other u's lie between the previous lane's last count (one shuffle) and its own, an
+// interval of ~nc/32 entries on average that a short forward scan resolves (the strided assignment of the first version
+// did nf/32 independent binary searches per lane: 28 bank-conflicting shared-memory reads instead of ~10).  The slope
+// delta0 / (w_{j+1} + 1e-7) is formed once per coarse bin (nc divisions per ray instead of nf) and the lane's outputs
+// leave as one 16-byte store when nf = 128.  Same operations on the same operands as before: idx / t_fine stay bit-exact.
 template <int EC>
 __global__ void __launch_bounds__(PDF_WARPS * 32)
     sample_pdf_kernel(int64_t n, int nf, const float* __restrict__ t_coarse, const float* __restrict__ w,
                       const float* __restrict__ delta0_ptr, float* __restrict__ t_fine, int32_t* __restrict__ idx_out,
                       int* __restrict__ status) {
   constexpr int NC = 32 * EC;
-  __shared__ float s_cdf[PDF_WARPS][NC], s_w[PDF_WARPS][NC], s_t[PDF_WARPS][NC];
+  __shared__ float s_cdf[PDF_WARPS][NC], s_w[PDF_WARPS][NC], s_t[PDF_WARPS][NC], s_slope[PDF_WARPS][NC];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ray = (int64_t)blockIdx.x * PDF_WARPS + wib;
   if (ray >= n) return;
   float* cdf = s_cdf[wib];
   float* wsm = s_w[wib];
   float* tc = s_t[wib];
+  float* slp = s_slope[wib];
 #pragma unroll
   for (int k = 0; k < EC; ++k) tc[lane * EC + k] = t_coarse[ray * NC + lane * EC + k];
   float lo, hi, step;
   build_cdf<EC>(w + ray * NC, cdf, wsm, lane, nf, lo, hi, step);
   const float delta0 = delta0_ptr ? *delta0_ptr : __fsub_rn(t_coarse[1], t_coarse[0]);  // ray 0 only (nerf.py:234)
+#pragma unroll
+  for (int k = 0; k < EC; ++k) {
+    const int j = lane * EC + k;
+    slp[j] = (j < NC - 1) ? __fdiv_rn(delta0, __fadd_rn(wsm[j + 1], 1e-7f)) : 0.f;
+  }
+  __syncwarp();
+  const int kf = nf >> 5;        // outputs per lane (nf is a multiple of 32, at most 224)
+  const int k0 = lane * kf;      // first output slot of this lane; u index = slot + 1
+  const float u_last = __fadd_rn(__fmul_rn((float)(k0 + kf), step), lo);
+  const int c_last = count_less<NC>(cdf, u_last);
+  int c = __shfl_up_sync(FULL, c_last, 1);
+  if (lane == 0) c = 0;
   bool bad = false;
-  for (int q = 0; q < nf / 32; ++q) {
-    int k = q * 32 + lane;  // output slot, u index k+1
-    float u = __fadd_rn(__fmul_rn((float)(k + 1), step), lo);
-    int j = count_less<NC>(cdf, u) - 1;
-    if (idx_out) idx_out[ray * nf + k] = j;
-    if (j < 0 || j > nf - 1) bad = true;  // nerf.py:251 compares against num_fine - 1
-    int jc = min(max(j, 0), NC - 1);
-    float slope = (jc < NC - 1) ? __fdiv_rn(delta0, __fadd_rn(wsm[jc + 1], 1e-7f)) : 0.f;
-    float tf = __fadd_rn(tc[jc], __fmul_rn(__fsub_rn(u, cdf[jc]), slope));
-    t_fine[ray * nf + k] = tf;
+  float tf[8];
+  int jj[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < kf) {
+      const float u = __fadd_rn(__fmul_rn((float)(k0 + i + 1), step), lo);
+      if (i == kf - 1) {
+        c = c_last;
+      } else {
+        while (c < c_last && cdf[c] < u) ++c;  // #{cdf < u}: every entry below c is < an earlier (smaller) u already
+      }
+      const int j = c - 1;
+      jj[i] = j;
+      if (j < 0 || j > nf - 1) bad = true;  // nerf.py:251 compares against num_fine - 1
+      const int jc = min(max(j, 0), NC - 1);
+      tf[i] = __fadd_rn(tc[jc], __fmul_rn(__fsub_rn(u, cdf[jc]), slp[jc]));
+    }
+  }
+  float* out = t_fine + ray * nf + k0;
+  if (kf == 4) {
+    *reinterpret_cast<float4*>(out) = make_float4(tf[0], tf[1], tf[2], tf[3]);
+    if (idx_out) *reinterpret_cast<int4*>(idx_out + ray * nf + k0) = make_int4(jj[0], jj[1], jj[2], jj[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < kf) {
+        out[i] = tf[i];
+        if (idx_out) idx_out[ray * nf + k0 + i] = jj[i];
+      }
   }
   if (__any_sync(FULL, bad) && lane == 0) atomicOr(status, 1);
 }
