@@ -72,7 +72,7 @@ extern "C" int nt_create(nt_ctx** out, int device, int n_coarse, int n_fine) {
     // measured on B200 (1024 / 4096 rays per step, gpurun_out/r2j_sweep*.log): 0 -> 1.508 / 5.133 ms, 72 -> 1.480 / 5.208,
     // 88 -> 1.466 / 5.003 (best), 96 -> 1.472 / 5.123, 112 -> 1.668 / 5.669: the HBM-bound launch needs ~60 % of the SMs
     const char* e = getenv("NT_DW_OVERLAP_CTAS");
-    c->opt_dw_overlap_ctas = e ? atoi(e) : (c->sm_count * 88) / 148;
+    c->opt_dw_overlap_ctas = e ? atoi(e) : (c->sm_count * 80) / 148;  // re-swept after the chain kernel got faster: 80 -> 1.31 / 4.66 ms, 88 -> 1.34 / 4.70
     if (c->opt_dw_overlap_ctas < 0 || c->opt_dw_overlap_ctas >= c->sm_count) c->opt_dw_overlap_ctas = 0;
   }
   c->last_delta = 1e-4f;
