@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
   if (threadIdx.x == 0) {
     if (sbase & 1023) __trap();
     for (int s = 0; s < N_STAGES; ++s) {
-      mbar_init(bar(BAR_W_FULL + s), 32);  // one cp.async-completion arrive per producer lane
+      mbar_init(bar(BAR_W_FULL + s), 1);
       mbar_init(bar(BAR_W_EMPTY + s), 1);
     }
     for (int tl = 0; tl < 2; ++tl) {
@@ -102,29 +102,27 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
 
   if (warp == WARP_TMA) {
     // ===================== weight producer =====================
-    // The whole warp copies each 32 KB chunk with 16-byte cp.async (LDGSTS) instead of one TMA bulk copy: the TMA unit of
-    // this SM is busy draining 128 KB of gradient-tile stores per step, and a bulk load queued behind them arrived 2 000 to
-    // 8 500 clk after it was issued (clock64 timeline) - the tensor core waited for weights in every step.  cp.async takes the
-    // LSU path, so weight loads and stash stores no longer share a queue.
-    uint32_t q = 0;
-    int pl = 0;
-    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pl) {
-      const uint8_t* src = P.packed + lane * 16;
-      for (int st = 0; st < N_STEPS; ++st)
-        for (int kc = 0; kc < step_chunks(st); ++kc, ++q) {
-          const uint32_t stage = q % N_STAGES;
-          mbar_wait(bar(BAR_W_EMPTY + stage), ((q / N_STAGES) & 1) ^ 1);
-          if (lane == 0 && kc == 1) BW_PROF(pl, st, 8);
-          if (lane == 0 && kc == 3) BW_PROF(pl, st, 9);
-          const uint32_t dst = sbase + OFF_W + stage * W_STAGE_BYTES + lane * 16;
-#pragma unroll 16
-          for (int i = 0; i < W_STAGE_BYTES / 512; ++i)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(src + i * 512) : "memory");
-          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar(BAR_W_FULL + stage)) : "memory");
-          src += W_STAGE_BYTES;
-        }
+    // TMA bulk copies with an evict_last L2 policy: ~9 KB of stash per sample stream through L2 while every CTA re-reads the
+    // same 1.1 MB of transposed weights; without the hint the stash evicted them and a 32 KB chunk took 2 000 - 8 500 clk to
+    // arrive (clock64 timeline), with it the weights stay L2-resident.
+    if (lane == 0) {
+      uint32_t q = 0;
+      int pl = 0;
+      const uint64_t pol_w = l2_policy_evict_last();
+      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pl) {
+        const uint8_t* src = P.packed;
+        for (int st = 0; st < N_STEPS; ++st)
+          for (int kc = 0; kc < step_chunks(st); ++kc, ++q) {
+            const uint32_t stage = q % N_STAGES;
+            mbar_wait(bar(BAR_W_EMPTY + stage), ((q / N_STAGES) & 1) ^ 1);
+            if (kc == 1) BW_PROF(pl, st, 8);
+            if (kc == 3) BW_PROF(pl, st, 9);
+            mbar_expect_tx(bar(BAR_W_FULL + stage), W_STAGE_BYTES);
+            tma_bulk_g2s_hint(sbase + OFF_W + stage * W_STAGE_BYTES, src, W_STAGE_BYTES, bar(BAR_W_FULL + stage), pol_w);
+            src += W_STAGE_BYTES;
+          }
+      }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer (+ the g_u operand loads) =====================
     if (lane == 0) {
@@ -136,7 +134,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
           for (int kc = 0; kc < nch; ++kc, ++q) {
             const uint32_t stage = q % N_STAGES;
             mbar_wait(bar(BAR_W_FULL + stage), (q / N_STAGES) & 1);
-            fence_proxy_async();  // the chunk was written through the generic proxy (cp.async), the tensor core reads it async
             tc_fence_after();
             const uint32_t b_addr = sbase + OFF_W + stage * W_STAGE_BYTES;
             BW_PROF(pl, st, 2 + kc);
@@ -231,6 +228,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
     const uint32_t wsig_s = sbase + OFF_WSIG;
     const int grp_bar = 1 + tl * 2 + half;                 // named barrier of this (tile, half) group
     const bool storer = (warp & 3) == 0 && lane == 0;      // the group's elected thread
+    const uint64_t pol_st = l2_policy_evict_first();       // stash lines leave L2 first (they are read once, much later)
     uint32_t it = 0;
     int pl = 0;
     const bool stamper = (warp & 3) == 0 && half == 0 && lane == 0;
@@ -293,7 +291,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
             asm volatile("bar.sync %0, 128;" ::"r"(grp_bar) : "memory");
             if (storer && row0 < P.total) {
               const int kc = half * 2 + (i >> 1);
-              tma_store_2d(&P.map_out[st], kc * 64, row0, act + kc * CHUNK_A_BYTES);
+              tma_store_2d_hint(&P.map_out[st], kc * 64, row0, act + kc * CHUNK_A_BYTES, pol_st);
               tma_store_commit();
             }
           }

@@ -533,6 +533,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dw_grouped_kernel(const __gri
   if (warp == 0) {
     if (lane == 0) {
       uint32_t q = 0;
+      const uint64_t pol_ld = l2_policy_evict_first();
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int pr, kb0, kb1;
         locate(item, pr, kb0, kb1);
@@ -542,8 +543,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dw_grouped_kernel(const __gri
           mbar_wait(bar(3 + s), ((q / DW_STAGES) & 1) ^ 1);
           mbar_expect_tx(bar(s), (a_boxes + b_boxes) * 8192);
           const uint32_t da = sbase + s * STAGE, db = da + DW_A_BYTES;
+          // the stash is read exactly once: evict_first keeps it from displacing the fp32 gradient the epilogues reduce into
+#ifdef NT_DW_NO_HINT
           for (int b = 0; b < a_boxes; ++b) tma_load_2d(da + b * 8192, &g.map_a[pr], b * 64, kb * BK, bar(s));
           for (int b = 0; b < b_boxes; ++b) tma_load_2d(db + b * 8192, &g.map_b[pr], b * 64, kb * BK, bar(s));
+#else
+          for (int b = 0; b < a_boxes; ++b) tma_load_2d_hint(da + b * 8192, &g.map_a[pr], b * 64, kb * BK, bar(s), pol_ld);
+          for (int b = 0; b < b_boxes; ++b) tma_load_2d_hint(db + b * 8192, &g.map_b[pr], b * 64, kb * BK, bar(s), pol_ld);
+#endif
         }
       }
     }

@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
     // ===================== TMA producer: weight K-chunks, same order for every tile pair =====================
     if (lane == 0) {
       uint32_t q = 0;
+      const uint64_t pol_w = l2_policy_evict_last();  // STASH: weights stay L2-resident under the stash stream (tc_ptx.cuh)
       for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
         const uint8_t* src = P.packed;
         for (int L = 0; L < N_MMA_LAYERS; ++L) {
@@ -267,7 +268,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
             const uint32_t stage = q & 1;
             mbar_wait(bar(BAR_W_EMPTY + stage), ((q >> 1) & 1) ^ 1);
             mbar_expect_tx(bar(BAR_W_FULL + stage), bytes);
-            tma_bulk_g2s(sbase + OFF_W + stage * W_STAGE_BYTES, src, bytes, bar(BAR_W_FULL + stage));
+            if (STASH)
+              tma_bulk_g2s_hint(sbase + OFF_W + stage * W_STAGE_BYTES, src, bytes, bar(BAR_W_FULL + stage), pol_w);
+            else
+              tma_bulk_g2s(sbase + OFF_W + stage * W_STAGE_BYTES, src, bytes, bar(BAR_W_FULL + stage));
             src += bytes;
           }
         }
@@ -278,6 +282,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
     if (lane == 0) {
       uint32_t q = 0, lit = 0;
       int pair_local = 0;
+      const uint64_t pol_st = l2_policy_evict_first();  // stash lines leave L2 first: they are read once, much later
       for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pair_local) {
         for (int L = 0; L < N_MMA_LAYERS; ++L, ++lit) {
           const int nch = layer_chunks(L);
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
                   // (legacy scheme, NT_STASH_MODE=3) layer 0's operand = the xyz features: stash them from smem
                   const int row0 = (pair * 2 + tl) * TILE_M;
                   if (row0 < P.total) {
-                    tma_store_2d(&P.st_map[9], 0, row0, sbase + OFF_ENC + tl * CHUNK_A_BYTES);
+                    tma_store_2d_hint(&P.st_map[9], 0, row0, sbase + OFF_ENC + tl * CHUNK_A_BYTES, pol_st);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                   }
                 }
@@ -323,9 +328,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
                 const int row0 = (pair * 2 + tl) * TILE_M;
                 if (row0 < P.total && (kc < 4 || L == 9)) {
                   if (kc < 4)
-                    tma_store_2d(&P.st_map[L - 1], kc * 64, row0, a_addr);
+                    tma_store_2d_hint(&P.st_map[L - 1], kc * 64, row0, a_addr, pol_st);
                   else
-                    tma_store_2d(&P.st_map[10], 0, row0, a_addr);
+                    tma_store_2d_hint(&P.st_map[10], 0, row0, a_addr, pol_st);
                   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
               }
