@@ -14,7 +14,7 @@ row, col, pix, pb, pic = synth.random_batch(rows17, n, 400, 400, torch.Generator
 flat = ops.flatten_state_dict(O.init_state_dict(624), dev)
 packed = ctx.pack(flat, prec)
 rays, _, de = ctx.raygen(row.to(dev), col.to(dev), pb.float().to(dev), synth.k_inv_of(400, 400, synth.focal_of(400)).to(dev))
-t = (torch.rand(n, 128, device=dev) * 4 + 2)
+t = (torch.rand(n, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 4 + 2)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for _ in range(3):
     ctx.mlp_forward(prec, t, rays, de, flat, packed)
