@@ -159,6 +159,26 @@ def test_mlp_fp16_vs_fp32(ctx, dev, n_rays):
         assert e16 < eb and s16 < sbb        # 3 more mantissa bits: strictly closer to fp32 than the bf16 operands
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_mlp_tc_run_to_run_bit_identical(ctx, dev, prec):
+    """The cta_group::2 schedule gives the same bits on every launch, also when two weight sets alternate and the image is
+    re-packed in place between launches (an experiment that kept the biases in constant memory failed exactly this: one
+    launch in ~40 computed a tile with the other weight set's stale biases)."""
+    from nerf_tiny_b200.ops import flatten_state_dict
+    code = FP16 if prec == "fp16" else BF16
+    t, rays, de = _mlp_inputs(ctx, dev, 2501)
+    ref = {}
+    for rep in range(6):
+        for w in ("trained64", "fern64_trained"):
+            flat = flatten_state_dict(sd_of(w), dev)
+            r, s, _ = ctx.mlp_forward(code, t, rays, de, flat, ctx.pack(flat, code))
+            torch.cuda.synchronize()
+            if w not in ref:
+                ref[w] = (r.clone(), s.clone())
+            else:
+                assert torch.equal(r, ref[w][0]) and torch.equal(s, ref[w][1]), (w, rep)
+
+
 def test_rendering_modes_refuse_training(ctx, dev):
     from nerf_tiny_b200 import _lib
     from nerf_tiny_b200.ops import flatten_state_dict
