@@ -254,6 +254,107 @@ class _RenderFn(torch.autograd.Function):
         return None, grads, None, None, None, None, None, None, None, None
 
 
+class _NetOutFn(torch.autograd.Function):
+    """net_out (nerf.py:179-222) as an autograd node: nt_mlp_forward with the training stash, nt_mlp_backward for the
+    parameter gradients and the gradient w.r.t. the sample positions t (nerf.py:200)."""
+
+    @staticmethod
+    def forward(ctx, model, flat, t, rays, denc):
+        prec = model._prec_train
+        n, p = t.shape
+        L, dev = model._lib, t.device
+        packed = model._pack(flat, prec)
+        need = L.nt_mlp_workspace_bytes(model._ctx, prec, n, p, 1)
+        ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        rgb = torch.empty(n, p, 3, device=dev)
+        sigma = torch.empty(n, p, device=dev)
+        _lib.check(L.nt_mlp_forward(model._ctx, prec, n, p, _ptr(t), _ptr(rays), _ptr(denc), _ptr(flat), _ptr(packed),
+                                    _ptr(rgb), _ptr(sigma), _ptr(ws), ws.numel(), 1, _stream(dev)))
+        ctx.model, ctx.ws, ctx.flat, ctx.t, ctx.rays, ctx.denc, ctx.rgb, ctx.prec = model, ws, flat, t, rays, denc, rgb, prec
+        return rgb, sigma.unsqueeze(-1)
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_sigma):
+        m, t = ctx.model, ctx.t
+        n, p = t.shape
+        dev = t.device
+        g_rgb = g_rgb.contiguous().float()
+        g_sigma = g_sigma.reshape(n, p).contiguous().float()
+        grads = torch.zeros_like(ctx.flat)
+        g_t = torch.empty(n, p, device=dev)
+        # the weights must be the ones the forward saw: re-pack (cheap) in case another call packed different ones since
+        packed = m._pack(ctx.flat, ctx.prec)
+        _lib.check(m._lib.nt_mlp_backward(m._ctx, ctx.prec, n, p, _ptr(t), _ptr(ctx.rays), _ptr(ctx.denc), _ptr(ctx.flat),
+                                          _ptr(packed), _ptr(ctx.rgb), _ptr(g_rgb), _ptr(g_sigma), _ptr(grads), _ptr(g_t),
+                                          _ptr(ctx.ws), ctx.ws.numel(), _stream(dev)))
+        ctx.ws = None
+        return None, grads, g_t, None, None
+
+
+class _DensityFn(torch.autograd.Function):
+    """get_density (nerf.py:263-272): forward = nt_get_density; backward in closed form with a = sigma * delta,
+    w_i = T_i (1 - e^{-a_i}), T_i = exp(-sum_{j<=i} a_j):  dL/da_j = g_j T_j e^{-a_j} - sum_{i>=j} g_i w_i."""
+
+    @staticmethod
+    def forward(ctx, model, delta, sigma):
+        n, p = delta.shape
+        w = torch.empty(n, p, dtype=torch.float32, device=delta.device)
+        _lib.check(model._lib.nt_get_density(model._ctx, n, p, _ptr(delta), _ptr(sigma), _ptr(w), _stream(delta.device)))
+        ctx.save_for_backward(delta, sigma, w)
+        return w
+
+    @staticmethod
+    def backward(ctx, g):
+        delta, sigma, w = ctx.saved_tensors
+        a = sigma * delta
+        T = torch.exp(-torch.cumsum(a.double(), -1)).float()
+        gw = g * w
+        tail = torch.flip(torch.cumsum(torch.flip(gw.double(), [-1]), -1), [-1]).float()   # sum_{i>=j} g_i w_i
+        g_a = g * T * torch.exp(-a) - tail
+        return None, g_a * sigma, g_a * delta
+
+
+class _ColorCumFn(torch.autograd.Function):
+    """color_cum (nerf.py:274-281): C = sum_i w_i rgb_i."""
+
+    @staticmethod
+    def forward(ctx, model, w, c):
+        n, p = w.shape
+        out = torch.empty(n, 3, dtype=torch.float32, device=w.device)
+        _lib.check(model._lib.nt_color_cum(model._ctx, n, p, _ptr(w), _ptr(c), _ptr(out), _stream(w.device)))
+        ctx.save_for_backward(w, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        w, c = ctx.saved_tensors
+        return None, (c * g[:, None, :]).sum(-1), w[..., None] * g[:, None, :]
+
+
+class _ResampleFn(torch.autograd.Function):
+    """resample (nerf.py:225-261): forward = nt_sample_pdf, backward = nt_sample_pdf_backward (the gradient
+    reaches the coarse weights through cdf[idx] and the slope; u, idx, delta0 and t_coarse carry none)."""
+
+    @staticmethod
+    def forward(ctx, model, t_coarse, w):
+        n = t_coarse.shape[0]
+        out = torch.empty(n, model.num_fine, device=t_coarse.device)
+        _lib.check(model._lib.nt_sample_pdf(model._ctx, n, _ptr(t_coarse), _ptr(w), None, _ptr(out), None, _stream(t_coarse.device)))
+        ctx.model = model
+        ctx.save_for_backward(t_coarse, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        t_coarse, w = ctx.saved_tensors
+        m = ctx.model
+        g = g.contiguous().float()
+        g_w = torch.empty_like(w)
+        _lib.check(m._lib.nt_sample_pdf_backward(m._ctx, t_coarse.shape[0], _ptr(t_coarse), _ptr(w), None, _ptr(g), _ptr(g_w),
+                                                 _stream(w.device)))
+        return None, None, g_w
+
+
 class NeRFModel(nn.Module):
     """nerf.py:169-348.  `precision` is the one extra knob (see PRECISION above; default "fp16", or $NERF_TINY_PRECISION).
 
@@ -445,7 +546,9 @@ class NeRFModel(nn.Module):
 
     # -- piecewise methods (same math, single kernels) ---------------------------------------------
     def net_out(self, t_array, batch_x, batch_y, trans_mat, K_inv, num_points):
-        """nerf.py:179-222 -> (color [N,P,3], sigma [N,P,1]); no autograd (use forward for training)."""
+        """nerf.py:179-222 -> (color [N,P,3], sigma [N,P,1]).  Differentiable like the reference's: with grad enabled and a
+        trainable network (or a t_array that requires grad) the call runs the training kernels (precision bf16, or fp32 for the
+        fp32 / tc32 models) and records an autograd node; otherwise the rendering kernels of `precision`."""
         dev = self._ensure_ctx()
         n = t_array.shape[0]
         t = _dev_f32(t_array, dev)
@@ -458,9 +561,13 @@ class NeRFModel(nn.Module):
         stride = 17 if pose.shape[-1] == 17 else pose[0].numel()
         _lib.check(self._lib.nt_raygen(self._ctx, n, _ptr(row), _ptr(col), _ptr(pose), stride, _ptr(kinv), _ptr(rays), None,
                                        _ptr(denc), _stream(dev)))
+        flat = self.network.flat_params()
+        t_grad = torch.is_tensor(t_array) and t_array.requires_grad
+        if torch.is_grad_enabled() and (t_grad or any(q.requires_grad for q in self.network.parameters())):
+            t_in = t_array.to(dev, torch.float32).contiguous() if t_grad else t
+            return _NetOutFn.apply(self, _FlatView.apply(flat, *self.network.parameters()), t_in, rays, denc)
         rgb = torch.empty(n, num_points, 3, device=dev)
         sigma = torch.empty(n, num_points, 1, device=dev)
-        flat = self.network.flat_params()
         packed = self._pack(flat, self._prec)
         need = self._lib.nt_mlp_workspace_bytes(self._ctx, self._prec, n, num_points, 0)
         ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
@@ -474,6 +581,8 @@ class NeRFModel(nn.Module):
         d, s_ = _dev_f32(delta, dev), _dev_f32(sigma, dev)
         if s_.dim() == 3:
             s_ = s_.squeeze(-1).contiguous()
+        if torch.is_grad_enabled() and (d.requires_grad or s_.requires_grad):
+            return _DensityFn.apply(self, d, s_)
         n, p = d.shape
         w = torch.empty(n, p, dtype=torch.float32, device=dev)
         _lib.check(self._lib.nt_get_density(self._ctx, n, p, _ptr(d), _ptr(s_), _ptr(w), _stream(dev)))
@@ -483,6 +592,8 @@ class NeRFModel(nn.Module):
         """nerf.py:274-281: C = sum_i w_i * rgb_i, [N,3]."""
         dev = self._ensure_ctx()
         w, c = _dev_f32(density, dev), _dev_f32(color, dev)
+        if torch.is_grad_enabled() and (w.requires_grad or c.requires_grad):
+            return _ColorCumFn.apply(self, w, c)
         n, p = w.shape
         out = torch.empty(n, 3, dtype=torch.float32, device=dev)
         _lib.check(self._lib.nt_color_cum(self._ctx, n, p, _ptr(w), _ptr(c), _ptr(out), _stream(dev)))
@@ -493,8 +604,11 @@ class NeRFModel(nn.Module):
         dev = self._ensure_ctx()
         t = _dev_f32(t_coarse, dev)
         w = _dev_f32(dense_coarse, dev)
-        out = torch.empty(t.shape[0], self.num_fine, device=dev)
-        _lib.check(self._lib.nt_sample_pdf(self._ctx, t.shape[0], _ptr(t), _ptr(w), None, _ptr(out), None, _stream(dev)))
+        if torch.is_grad_enabled() and w.requires_grad:
+            out = _ResampleFn.apply(self, t, w)
+        else:
+            out = torch.empty(t.shape[0], self.num_fine, device=dev)
+            _lib.check(self._lib.nt_sample_pdf(self._ctx, t.shape[0], _ptr(t), _ptr(w), None, _ptr(out), None, _stream(dev)))
         self.check_status()
         return out
 

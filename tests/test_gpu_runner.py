@@ -152,6 +152,72 @@ def test_get_density_and_color_cum_methods():
         model.get_density(delta[:, :100], sigma[:, :100])                         # not a multiple of 32
 
 
+def test_piecewise_methods_are_differentiable():
+    """The reference's piecewise methods are ordinary autograd code (nerf.py:179-281); here get_density / color_cum /
+    resample / net_out record autograd nodes whose gradients match fp64 autograd of the oracle on the same inputs."""
+    import numpy as np
+    from nerf_tiny_b200 import nerf, synth
+    from oracle import nerf_oracle as O
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(5)
+    model = nerf.NeRFModel(batch_ray=8, precision="fp32").to(dev)
+    # ---- get_density + color_cum chained, gradients w.r.t. delta, sigma, colour
+    delta = (torch.rand(19, 64, generator=gen) * 0.06 + 1e-3)
+    sigma = torch.rand(19, 64, generator=gen) * 8
+    color = torch.rand(19, 64, 3, generator=gen)
+    seed = torch.rand(19, 3, generator=gen)
+    d, s_, c = (x.clone().to(dev).requires_grad_(True) for x in (delta, sigma, color))
+    out = model.color_cum(model.get_density(d, s_), c)
+    (out * seed.to(dev)).sum().backward()
+    d64, s64, c64 = (x.double().requires_grad_(True) for x in (delta, sigma, color))
+    (O.color_cum(O.get_density(d64, s64), c64) * seed.double()).sum().backward()
+    for got, ref in ((d.grad, d64.grad), (s_.grad, s64.grad), (c.grad, c64.grad)):
+        assert float((got.cpu().double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    # ---- resample, gradient w.r.t. the coarse weights (no gradient to t_coarse, like the reference)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fern64.npz"))
+    t_c, w_c = torch.from_numpy(g["t_coarse"]), torch.from_numpy(g["w_c"])
+    seed = torch.rand(t_c.shape[0], 128, generator=gen)
+    w_dev = w_c.clone().to(dev).requires_grad_(True)
+    (model.resample(t_c, w_dev) * seed.to(dev)).sum().backward()
+    w64 = w_c.double().requires_grad_(True)
+    t_ref, idx, u, cdf = O.resample(t_c.double(), w64, 128, return_aux=True)
+    (t_ref * seed.double()).sum().backward()
+    # the fp32 kernel and the fp64 oracle agree on idx for this fixture (checked bit-exactly elsewhere); the factor
+    # delta0 / (w + 1e-7)^2 makes single entries huge, hence the relative measure
+    assert float((w_dev.grad.cpu().double() - w64.grad).abs().max()) <= 2e-3 * float(w64.grad.abs().max())
+    # ---- net_out: parameter gradients and the gradient w.r.t. t (fp32 model -> fp32 training kernels)
+    sd = O.init_state_dict(624)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    h = w = 100
+    f = synth.focal_of(w)
+    rows17 = synth.pose_rows(8, h, w, f)
+    k_inv = synth.k_inv_of(h, w, f)
+    row, col, pix, pb, pic = synth.random_batch(rows17, 12, h, w, gen)
+    c2w = O.poses_extract(pb)[0]
+    t = (torch.rand(12, 32, generator=gen) * 4 + 2)
+    t_dev = t.clone().to(dev).requires_grad_(True)
+    sr, ss = torch.rand(12, 32, 3, generator=gen), torch.rand(12, 32, 1, generator=gen)
+    col_g, sig_g = model.net_out(t_dev, row, col, pb, k_inv, 32)
+    assert col_g.shape == (12, 32, 3) and sig_g.shape == (12, 32, 1)
+    ((col_g * sr.to(dev)).sum() + (sig_g * ss.to(dev)).sum()).backward()
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    d_cam, d_wrd = O.ray_dirs(row.numpy(), col.numpy(), k_inv.numpy(), c2w.numpy())
+    t64 = t.double().requires_grad_(True)
+    c_ref, s_ref = O.net_out(sd64, t64, d_cam.astype(np.float64), d_wrd.astype(np.float64), c2w.numpy().astype(np.float64),
+                             faithful32=True)
+    ((c_ref * sr.double()).sum() + (s_ref.unsqueeze(-1) * ss.double()).sum()).backward()
+    assert float((col_g.detach().cpu().double() - c_ref.detach()).abs().max()) <= 1e-4
+    rel = lambda got, ref: float((got.cpu().double() - ref).norm() / ref.norm().clamp_min(1e-20))
+    # d enc / dt carries frequencies up to 3217 with cancellation (SURVEY.md §4.1): same bound as test_mlp_fp32_backward
+    assert rel(t_dev.grad, t64.grad) <= 2e-2
+    for name, prm in model.named_parameters():
+        assert rel(prm.grad, sd64[name].grad) <= 2e-3, name
+    # without grad the same calls take the rendering kernels and record nothing
+    with torch.no_grad():
+        assert not model.net_out(t, row, col, pb, k_inv, 32)[0].requires_grad
+
+
 def test_encoder_and_network_standalone_modules():
     """Encoder.forward / Network.forward called the way the reference exposes them (nerf.py:101-167), against the outputs
     the unmodified reference wrote for the same inputs and weights (tests/golden/encoder_network.npz)."""
