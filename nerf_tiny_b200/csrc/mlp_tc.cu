@@ -1087,6 +1087,10 @@ int nt_mlp_tc_pack(nt_ctx* ctx, const float* params, void* packed, int mode, cud
   return NT_OK;
 }
 
+static float* g_fwd_prof = nullptr;
+// diagnostics only (tools/fwd_stash_timeline.py): device buffer of 4 * 10 * 16 int64 that the next stash-forward launches stamp
+extern "C" void nt_debug_set_fwd_prof(void* p) { g_fwd_prof = (float*)p; }
+
 static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const float* rays, const float* dir_enc,
                          const float* params, const void* packed, float* rgb, float* sigma, float* dbg, int dbg_layer,
                          const TcStash* stash, int fp16, cudaStream_t st) {
@@ -1173,7 +1177,12 @@ static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const fl
     NT_LAUNCH_CHECK(ctx);
     return NT_OK;
   }
-  if (stash)
+  if (stash && g_fwd_prof) {
+    NT_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    P.dbg = g_fwd_prof;
+    P.dbg_layer = 100;
+    mlp_tc_kernel<true, true><<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
+  } else if (stash)
     mlp_tc_kernel<false, true><<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
   else if (dbg)
     mlp_tc_kernel<true, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
