@@ -68,6 +68,8 @@ extern "C" int nt_create(nt_ctx** out, int device, int n_coarse, int n_fine) {
   c->side = nullptr;
   c->ev_fork = c->ev_join = nullptr;
   c->defer_dw = c->dw_pending = 0;
+  c->shared_wb = nullptr;
+  c->share_wb = 0;
   {
     // measured on B200 (1024 / 4096 rays per step, gpurun_out/r2j_sweep*.log): 0 -> 1.508 / 5.133 ms, 72 -> 1.480 / 5.208,
     // 88 -> 1.466 / 5.003 (best), 96 -> 1.472 / 5.123, 112 -> 1.668 / 5.669: the HBM-bound launch needs ~60 % of the SMs
@@ -329,9 +331,12 @@ extern "C" int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const f
   // fine MLP: dW + input gradient down to t_fine (B.4, B.6, B.7)
   const bool detach = ctx->opt_detach_t_fine != 0;
   ctx->defer_dw = (precision == NT_PREC_BF16 && ctx->opt_dw_overlap_ctas > 0) ? 1 : 0;
+  ctx->share_wb = 1;  // both passes use the same parameters: pack the transposed weights once
+  ctx->shared_wb = nullptr;
   int rc_fine = nt_mlp_backward(ctx, precision, n, nf, w.t_f, w.rays, w.dir_enc, params, packed, w.rgb_f, w.g_rgb_f, w.g_sig_f, grads,
                                 detach ? nullptr : w.g_t_mlp, w.mlp_f, w.mlp_f_bytes, stream);
   ctx->defer_dw = 0;
+  if (rc_fine != NT_OK) ctx->share_wb = 0;
   NT_TRY(rc_fine);
   // g_t_fine = compositing path + MLP-input path (summed inside the kernel); then resample backward (B.5)
   if (!detach)
@@ -340,8 +345,11 @@ extern "C" int nt_render_backward(nt_ctx* ctx, int precision, int64_t n, const f
   NT_TRY(nt_launch_composite_coarse_backward(ctx, n, near_, far_, w.rgb_c, w.sig_c, g_c_coarse, detach ? nullptr : w.g_w_c,
                                              w.g_rgb_c, w.g_sig_c, 1, (cudaStream_t)stream));
   // coarse MLP: dW only (t_coarse is a constant)
-  NT_TRY(nt_mlp_backward(ctx, precision, n, nc, w.t_c, w.rays, w.dir_enc, params, packed, w.rgb_c, w.g_rgb_c, w.g_sig_c, grads,
-                         nullptr, w.mlp_c, w.mlp_c_bytes, stream));
+  int rc_coarse = nt_mlp_backward(ctx, precision, n, nc, w.t_c, w.rays, w.dir_enc, params, packed, w.rgb_c, w.g_rgb_c, w.g_sig_c,
+                                  grads, nullptr, w.mlp_c, w.mlp_c_bytes, stream);
+  ctx->share_wb = 0;
+  ctx->shared_wb = nullptr;
+  NT_TRY(rc_coarse);
   NT_TRY(nt_join_deferred_dw(ctx, (cudaStream_t)stream));
   return NT_OK;
 }

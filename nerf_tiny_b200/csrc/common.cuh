@@ -29,6 +29,10 @@ struct nt_ctx {
   int opt_dw_overlap_ctas;  // 0 = off
   int defer_dw;             // set by nt_render_backward around the fine pass
   int dw_pending;           // a deferred launch has not been joined yet
+  // nt_render_backward packs the transposed weights once: the fine pass packs into its workspace and leaves the pointer here
+  // for the coarse pass (same parameters); -1 = not inside nt_render_backward (every nt_mlp_backward call packs for itself)
+  const void* shared_wb;
+  int share_wb;
   unsigned attr_done;  // NT_ATTR_*: cudaFuncSetAttribute is per DEVICE, so the "already opted in" bits live in the ctx
 };
 enum {

@@ -266,7 +266,13 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
   NT_TRY(dW(w.Gu, 128, 128, H[8], 256, 256, G + T.w[L_DIR] + 24, 280));
   // fused backward-data chain: g_u -> g_info -> g_7 .. g_0 in one tcgen05 kernel (bwd_tc.cu); also the bias gradients
   {
-    NT_TRY(nt_bwd_tc_pack(ctx, P, w.WB, st));
+    const void* WB = w.WB;
+    if (ctx->share_wb && ctx->shared_wb) {
+      WB = ctx->shared_wb;  // packed by the fine pass of this nt_render_backward call (same parameters, same stream)
+    } else {
+      NT_TRY(nt_bwd_tc_pack(ctx, P, w.WB, st));
+      if (ctx->share_wb) ctx->shared_wb = w.WB;
+    }
     void* outs[9] = {w.GI, w.GS[7], w.GS[6], w.GS[5], w.GS[4], w.GS[3], w.GS[2], w.GS[1], w.GS[0]};
     float* dbs[9] = {G + T.b[L_INFO], G + T.b[L_P7], G + T.b[L_P6], G + T.b[L_P5], G + T.b[L_P4],
                      G + T.b[L_P3],   G + T.b[L_P2], G + T.b[L_P1], G + T.b[L_P0]};
@@ -274,7 +280,7 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
     // while a deferred weight-gradient launch of the previous pass is still running on the side stream, this MMA-bound
     // kernel takes only the SMs that launch leaves free
     const int cap = ctx->dw_pending ? ctx->sm_count - ctx->opt_dw_overlap_ctas : 0;
-    NT_TRY(nt_bwd_tc_chain(ctx, S, w.Gu, outs, lds, w.WB, cap, w.st.bits, w.gzsig, P + T.w[L_SIGMA], dbs, st));
+    NT_TRY(nt_bwd_tc_chain(ctx, S, w.Gu, outs, lds, WB, cap, w.st.bits, w.gzsig, P + T.w[L_SIGMA], dbs, st));
     if (ctx->defer_dw) NT_CUDA(cudaEventRecord(ctx->ev_fork, st));  // every operand of this pass's dW problems is complete here
   }
   // weight gradients (queued): point_info, sigma head, trunk
