@@ -192,6 +192,13 @@ struct GemmTcEpi {
   const float* r1_row;  // optional rank-1 term added before the mask: v += r1_row[m] * r1_col[n]
   const float* r1_col;
   float* colsum;        // optional fp32 [N]: += column sums of the stored matrix (fused bias gradient)
+  // optional fused encoder backward (N = 64 only): the fp32 row is the gradient w.r.t. the 60 xyz features of sample m; instead
+  // of storing it, g_t[m] += sum_c d_wrd_c * sum_l w_l (g_sin cos(w_l p_c) - g_cos sin(w_l p_c))  (SURVEY.md B.4).  enc_gt must
+  // be zero on entry (the two column halves of a row add their parts with one atomic each).
+  const float* enc_t;     // [M] sample positions t
+  const float* enc_rays;  // ray records [M / enc_p][16]
+  int enc_p;              // samples per ray
+  float* enc_gt;          // [M] or null
 };
 int nt_launch_gemm_tc(nt_ctx* ctx, int mn_major, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                       const GemmTcEpi& epi, cudaStream_t st);

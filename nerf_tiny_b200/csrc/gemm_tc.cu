@@ -41,7 +41,51 @@ struct GemmTcArgs {
   const float* r1_row;  // rank-1 term v += r1_row[m] * r1_col[n] (sigma-head gradient joining point_info's)
   const float* r1_col;
   float* colsum;        // optional [N]: += column sums of the stored matrix (bias gradient of the layer below)
+  const float* enc_t;   // epi == 3: fused encoder backward (GemmTcEpi)
+  const float* enc_rays;
+  int enc_p;
+  float* enc_gt;
 };
+
+// epi == 3: this thread holds g_enc[m][n0 .. n0+31] (n0 = 0 or 32) of sample m; features f = c*20 + 2l + {sin, cos}
+__device__ __forceinline__ void enc_backward_part(const GemmTcArgs& g, int m, int n0, const float (&v)[32]) {
+  constexpr uint32_t kFreq[10] = NT_FREQ_POINT_INIT;
+  const float* ray = g.enc_rays + (int64_t)(m / g.enc_p) * 16;
+  float r[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(ray) + q);
+    r[4 * q] = x.x; r[4 * q + 1] = x.y; r[4 * q + 2] = x.z; r[4 * q + 3] = x.w;
+  }
+  const float t = __ldg(g.enc_t + m);
+  // p_cam = fl(d_cam * t); p_wrd = ((R0 p0 + R1 p1) + R2 p2) + T, no FMA (nerf.py:200-216); d_wrd likewise (nerf.py:211)
+  const float pc0 = __fmul_rn(r[0], t), pc1 = __fmul_rn(r[1], t), pc2 = __fmul_rn(r[2], t);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    // (c, l) pairs whose two features fall into this half: half 0 -> c = 0 (all l), c = 1 (l < 6); half 1 -> c = 1 (l >= 6), c = 2
+    const int l_lo = n0 == 0 ? 0 : (c == 1 ? 6 : 0), l_hi = n0 == 0 ? (c == 0 ? 10 : (c == 1 ? 6 : 0)) : (c == 0 ? 0 : 10);
+    if (l_lo >= l_hi) continue;
+    const float pos = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[3 + c * 3], pc0), __fmul_rn(r[4 + c * 3], pc1)),
+                                          __fmul_rn(r[5 + c * 3], pc2)), r[12 + c]);
+    const float dw = __fadd_rn(__fadd_rn(__fmul_rn(r[3 + c * 3], r[0]), __fmul_rn(r[4 + c * 3], r[1])), __fmul_rn(r[5 + c * 3], r[2]));
+    float gp = 0.f;
+#pragma unroll
+    for (int l = 0; l < 10; ++l) {
+      if (l < l_lo || l >= l_hi) continue;
+      const float w = __uint_as_float(kFreq[l]);
+      const float x = __fmul_rn(w, pos);
+      const float k = __fadd_rn(__fmaf_rn(x, 0.15915494309189535f, 12582912.f), -12582912.f);
+      float rr = fmaf(k, -6.2831854820251465f, x);
+      rr = fmaf(k, 1.7484555314695172e-07f, rr);
+      const float sn = __sinf(rr), cs = __cosf(rr);
+      const int f = c * 20 + 2 * l - n0;  // compile-time after unrolling (n0 selects one of two instantiations below)
+      gp += w * (v[f] * cs - v[f + 1] * sn);
+    }
+    acc += gp * dw;
+  }
+  atomicAdd(g.enc_gt + m, acc);
+}
 
 // PTX wrappers: tc_ptx.cuh
 using namespace tcptx;
@@ -299,6 +343,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                   if (!(hi != 0 && hi < 0x8000u)) v[qd * 8 + k2 * 2 + 1] = 0.f;
                 }
               }
+            }
+            if (g.epi == 3) {
+              if (n0 == 0)
+                enc_backward_part(g, m, 0, v);
+              else if (n0 == 32)
+                enc_backward_part(g, m, 32, v);
+              continue;
             }
             if (g.epi == 2) {
               float* cf = reinterpret_cast<float*>(g.C) + (int64_t)m * g.ldc + n0;
@@ -691,7 +742,15 @@ int nt_launch_gemm_tc(nt_ctx* ctx, int mn_major, int M, int N, int K, const void
   g.N = BN;
   g.K = K;
   g.n_valid = N;
-  g.epi = epi.atomic_f32 ? 1 : (epi.store_f32 ? 2 : 0);
+  g.epi = epi.enc_gt ? 3 : (epi.atomic_f32 ? 1 : (epi.store_f32 ? 2 : 0));
+  if (epi.enc_gt && (N != 64 || mn_major || epi.atomic_f32)) {
+    nt_set_error("gemm_tc: the fused encoder backward needs N = 64, K-major operands and no split-K");
+    return NT_ERR_INVALID;
+  }
+  g.enc_t = epi.enc_t;
+  g.enc_rays = epi.enc_rays;
+  g.enc_p = epi.enc_p;
+  g.enc_gt = epi.enc_gt;
   g.r1_row = epi.r1_row;
   g.r1_col = epi.r1_col;
   g.colsum = epi.colsum;

@@ -294,12 +294,15 @@ int nt_mlp_bf16_train_backward(nt_ctx* ctx, int64_t n, int p, const float* t, co
   if (g_t) {
     // fp32 gradient w.r.t. the xyz features, skip connection and first layer in ONE GEMM over [g_4 | g_0] (K = 512), then
     // down to t through the encoder (B.7)
+    // the encoder backward runs in the GEMM's epilogue (each thread holds half of a sample's 60 feature gradients): the fp32
+    // [S][64] feature gradient never goes to HBM (256 B written + read per sample and one launch less)
     GemmTcEpi e = epi0();
-    e.C = w.genc;
-    e.ldc = 64;
-    e.store_f32 = 1;
+    e.enc_t = t;
+    e.enc_rays = rays;
+    e.enc_p = p;
+    e.enc_gt = g_t;
+    NT_CUDA(cudaMemsetAsync(g_t, 0, (size_t)S * sizeof(float), st));
     NT_TRY(nt_launch_gemm_tc(ctx, 0, S, 64, 512, w.GS[4], 512, w.WT, 512, e, st));
-    NT_TRY(nt_launch_encode_backward(ctx, n, p, t, rays, w.genc, 64, g_t, st));
   }
   if (ctx->defer_dw) {
     // fork: the HBM-bound contraction of this (fine) pass runs on the side stream with a capped grid, next to the
