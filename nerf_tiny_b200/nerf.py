@@ -766,8 +766,8 @@ class GraphedTrainStep:
         self.col = torch.zeros(self.n, dtype=torch.int64, device=dev)
         self.pix = torch.zeros(self.n, 3, dtype=torch.float32, device=dev)
         self.pb = torch.zeros(self.n, 17, dtype=torch.float32, device=dev)
-        self.near = torch.zeros(self.n, dtype=torch.float32, device=dev)
-        self.far = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self._nf = torch.zeros(2, self.n, dtype=torch.float32, device=dev)   # near / far rows, filled by ONE strided copy
+        self.near, self.far = self._nf[0], self._nf[1]
         self.kinv = _dev_f32(K_inv, dev)
         # batch-global quantities of a sharded batch live in a static buffer the captured kernels read
         self.g = torch.zeros(4, dtype=torch.float32, device=dev) if shard is not None else None
@@ -818,8 +818,7 @@ class GraphedTrainStep:
         self.col.copy_(column, non_blocking=True)
         self.pix.copy_(pix_val, non_blocking=True)
         self.pb.copy_(poses_bound, non_blocking=True)      # float64 loader rows are converted by the copy (nerf.py:338)
-        self.near.copy_(self.pb[:, 15])
-        self.far.copy_(self.pb[:, 16])
+        self._nf.copy_(self.pb[:, 15:17].t())
         if self.g is not None:
             _, g = self.model._globals(self.shard, self.near, self.far)
             self.g.copy_(g)
