@@ -11,6 +11,7 @@
 // tile is also stashed to HBM by TMA tensor stores for the grouped weight-gradient GEMM (gemm_tc.cu).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -51,6 +52,7 @@ struct BwdParams {
   float* db[N_STEPS];             // bias gradients: point_info, layer 7 .. layer 0
   int64_t total;
   int num_pairs;
+  int num_items, full_pairs;      // work items: pairs below full_pairs, then single tiles (see mlp_tc.cu TcParams)
   long long* prof;                // optional clock64 timeline of block 0's first pairs (tools/chain_timeline.py)
 };
 
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
       uint32_t q = 0;
       int pl = 0;
       const uint64_t pol_w = l2_policy_evict_last();
-      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pl) {
+      for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++pl) {
         const uint8_t* src = P.packed;
         for (int st = 0; st < N_STEPS; ++st)
           for (int kc = 0; kc < step_chunks(st); ++kc, ++q) {
@@ -128,7 +130,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(256);
       uint32_t q = 0, lit = 0, pl = 0;
-      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pl) {
+      for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++pl) {
+        // a single-tile item is always this CTA's last one: tile B's barrier phases may fall behind `lit` from there on
+        const bool single = item >= P.full_pairs;
+        const int tile0 = single ? 2 * P.full_pairs + (item - P.full_pairs) : 2 * item;
+        const int ntl = single ? 1 : 2;
         for (int st = 0; st < N_STEPS; ++st, ++lit) {
           const int nch = step_chunks(st);
           for (int kc = 0; kc < nch; ++kc, ++q) {
@@ -139,6 +145,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
             BW_PROF(pl, st, 2 + kc);
 #pragma unroll
             for (int tl = 0; tl < 2; ++tl) {
+              if (tl >= ntl) continue;
               const uint32_t act = sbase + OFF_ACT + tl * ACT_BYTES;
               if (kc == 0) {
                 mbar_wait(bar(BAR_ACT_READY + tl), lit & 1);  // epilogue done: operand in place, accumulator drained
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
                   // fetch this pair's g_u tile over the previous pair's g_0 tile: its stash stores have left shared memory
                   // (the epilogue's storing threads wait for that before the arrive of the last step) and its column sums
                   // have been taken
-                  const int row0 = (pair * 2 + tl) * TILE_M;
+                  const int row0 = (tile0 + tl) * TILE_M;
                   if (lit > 0) mbar_wait(bar(BAR_CS_DONE + tl), (lit - 1) & 1);
                   mbar_expect_tx(bar(BAR_A_FULL + tl), 2 * CHUNK_A_BYTES);
                   tma_load_2d(act, &P.map_gu, 0, row0, bar(BAR_A_FULL + tl));
@@ -183,7 +190,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
     const int j = lane & 7;
     uint32_t it = 0;
     mbar_wait(bar(BAR_ACT_READY + tl), 0);  // completion #0 is the epilogue warps' start-up arrive (no data behind it)
-    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
+      if (item >= P.full_pairs && tl == 1) break;  // single-tile item: no tile B
       for (int st = 0; st < N_STEPS; ++st, ++it) {
         mbar_wait(bar(BAR_ACT_READY + tl), (it + 1) & 1);  // completion #it+1: the output of step `it` is in place
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -233,8 +241,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_tc_kernel(const __grid_const
     int pl = 0;
     const bool stamper = (warp & 3) == 0 && half == 0 && lane == 0;
     mbar_arrive(bar(BAR_ACT_READY + tl));  // nothing to protect before the first pair
-    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pl) {
-      const int row0 = (pair * 2 + tl) * TILE_M;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++pl) {
+      const bool single = item >= P.full_pairs;
+      if (single && tl == 1) break;  // single-tile item (this CTA's last): tile B's warps have nothing to do
+      const int row0 = ((single ? 2 * P.full_pairs + (item - P.full_pairs) : 2 * item) + tl) * TILE_M;
       const int64_t s = (int64_t)row0 + row;
       const bool valid = s < P.total;
       const float gz = valid ? __ldg(P.gzsig + s) : 0.f;
@@ -404,8 +414,19 @@ int nt_bwd_tc_chain(nt_ctx* ctx, int64_t S, const void* g_u, void* const outs[9]
   P.prof = g_chain_prof;
   const int64_t tiles = (S + TILE_M - 1) / TILE_M;
   P.num_pairs = (int)((tiles + 1) / 2);
-  int grid = ctx->sm_count < P.num_pairs ? ctx->sm_count : P.num_pairs;
-  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;  // leave SMs to a concurrent launch on another stream
+  int G = ctx->sm_count;
+  if (max_ctas > 0 && max_ctas < G) G = max_ctas;  // leave SMs to a concurrent launch on another stream
+  // tile pairs, except that a last wave which would occupy at most half of the CTAs runs as single tiles
+  P.full_pairs = P.num_pairs;
+  P.num_items = P.num_pairs;
+  {
+    const int64_t waves = tiles / (2 * (int64_t)G), rest = tiles - 2 * (int64_t)G * waves;
+    if (rest > 0 && rest <= G && !getenv("NT_NO_SINGLE_TILES")) {
+      P.full_pairs = (int)(G * waves);
+      P.num_items = (int)(G * waves + rest);
+    }
+  }
+  const int grid = G < P.num_items ? G : P.num_items;
   bwd_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(P);
   NT_LAUNCH_CHECK(ctx);
   return NT_OK;

@@ -41,6 +41,10 @@ struct TcParams {
   int p;          // samples per ray
   int p_shift;    // log2(p) when p is a power of two, else -1
   int num_pairs;
+  // lock-step kernel: work items.  Items below full_pairs are tile pairs (tiles 2i, 2i+1); the remaining items are SINGLE
+  // tiles (tile 2*full_pairs + (i - full_pairs)) - used when the last wave of pairs would leave more than half of the CTAs
+  // idle (the 1024-ray training batch: 512 fine-pass pairs = 3 waves of 148 + 68 pairs -> 136 single tiles on 136 CTAs)
+  int num_items, full_pairs;
   // training stash (STASH instantiation): bf16 activations kept in HBM for the layer-major backward
   __nv_bfloat16* st[N_MMA_LAYERS];  // post-activation output of every tensor-core layer, [S][256] ([S][128] for dir_info)
   __nv_bfloat16* st_enc;            // xyz features [S][64] (60 + zero pad)
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
     if (lane == 0) {
       uint32_t q = 0;
       const uint64_t pol_w = l2_policy_evict_last();  // STASH: weights stay L2-resident under the stash stream (tc_ptx.cuh)
-      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x) {
+      for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
         const uint8_t* src = P.packed;
         for (int L = 0; L < N_MMA_LAYERS; ++L) {
           const uint32_t bytes = chunk_bytes(L);
@@ -283,7 +287,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
       uint32_t q = 0, lit = 0;
       int pair_local = 0;
       const uint64_t pol_st = l2_policy_evict_first();  // stash lines leave L2 first: they are read once, much later
-      for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pair_local) {
+      for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++pair_local) {
+        // a single-tile item is always this CTA's LAST item, so tile B's barrier phases may fall behind `lit` from here on
+        const bool single = item >= P.full_pairs;
+        const int tile0 = single ? 2 * P.full_pairs + (item - P.full_pairs) : 2 * item;
+        const int ntl = single ? 1 : 2;
         for (int L = 0; L < N_MMA_LAYERS; ++L, ++lit) {
           const int nch = layer_chunks(L);
           const uint32_t idesc = umma_idesc(layer_n(L));
@@ -294,19 +302,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
             const uint32_t b_addr = sbase + OFF_W + stage * W_STAGE_BYTES;
 #pragma unroll
             for (int tl = 0; tl < 2; ++tl) {
+              if (tl >= ntl) continue;
               if (kc == 0) {  // A operand written + accumulator drained by the tile's epilogue warps
                 mbar_wait(bar(BAR_ACT_READY + tl), lit & 1);
                 tc_fence_after();
                 TC_PROF(tl);
                 if (STASH && P.use_tma_stash == 3 && L == 0) {
                   // (legacy scheme, NT_STASH_MODE=3) layer 0's operand = the xyz features: stash them from smem
-                  const int row0 = (pair * 2 + tl) * TILE_M;
+                  const int row0 = (tile0 + tl) * TILE_M;
                   if (row0 < P.total) {
                     tma_store_2d_hint(&P.st_map[9], 0, row0, sbase + OFF_ENC + tl * CHUNK_A_BYTES, pol_st);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                   }
                 }
-                if (tl == 1) {
+                if (tl == ntl - 1) {
                   // every epilogue thread is done with the previous layer's record: stage this layer's biases / head
                   // weights (1-2.5 KB) for the epilogue that follows these MMAs
                   mbar_expect_tx(bar(BAR_AUX_FULL), aux_bytes(L));
@@ -325,7 +334,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
                 // this K-chunk of the operand = 64 columns of the previous layer's bf16 output (chunk 4 of dir_info = the
                 // view features): stash it from smem.  One 16 KB box per chunk step, not the whole tile at once, so the
                 // weight loads of the next chunks are not queued behind 128 KB of stores in the TMA unit.
-                const int row0 = (pair * 2 + tl) * TILE_M;
+                const int row0 = (tile0 + tl) * TILE_M;
                 if (row0 < P.total && (kc < 4 || L == 9)) {
                   if (kc < 4)
                     tma_store_2d_hint(&P.st_map[L - 1], kc * 64, row0, a_addr, pol_st);
@@ -371,9 +380,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_tc_kernel(const __grid_const
     const bool tma_stash = STASH && P.use_tma_stash == 1;
     const bool stasher = tma_stash && (warp & 3) == 0 && half == 0 && lane == 0;
     const int tile_bar = 9 + tl;
-    for (int pair = blockIdx.x; pair < P.num_pairs; pair += gridDim.x, ++pair_local) {
-      const int row0 = (pair * 2 + tl) * TILE_M;
-      const int64_t s = ((int64_t)pair * 2 + tl) * TILE_M + row;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++pair_local) {
+      const bool single = item >= P.full_pairs;
+      if (single && tl == 1) break;  // single-tile item (this CTA's last): tile B's warps have nothing to do
+      const int tile0 = single ? 2 * P.full_pairs + (item - P.full_pairs) : 2 * item;
+      const int row0 = (tile0 + tl) * TILE_M;
+      const int64_t s = ((int64_t)tile0 + tl) * TILE_M + row;
       const bool valid = s < P.total;
       const int64_t sc = valid ? s : P.total - 1;
       const int64_t ray = sc / P.p;
@@ -1145,7 +1157,17 @@ static int mlp_tc_launch(nt_ctx* ctx, int64_t n, int p, const float* t, const fl
   const int64_t tiles = (P.total + TILE_M - 1) / TILE_M;
   P.num_pairs = (int)((tiles + 1) / 2);
   if (P.num_pairs == 0) return NT_OK;
-  int grid = ctx->sm_count < P.num_pairs ? ctx->sm_count : P.num_pairs;
+  // lock-step kernel: tile pairs, except that a last wave which would occupy at most half of the CTAs runs as single tiles
+  P.full_pairs = P.num_pairs;
+  P.num_items = P.num_pairs;
+  {
+    const int64_t G = ctx->sm_count, waves = tiles / (2 * G), rest = tiles - 2 * G * waves;
+    if (rest > 0 && rest <= G && !getenv("NT_NO_SINGLE_TILES")) {
+      P.full_pairs = (int)(G * waves);
+      P.num_items = (int)(G * waves + rest);
+    }
+  }
+  int grid = ctx->sm_count < P.num_items ? ctx->sm_count : P.num_items;
   // schedule variants (NT_OPT_MLP_TC_VERSION / env NT_MLP_TC_VERSION): 5 = tile pair in lock-step (the training
   // instantiation and the per-layer debug dump always use it), 6 = staggered tiles + 2-CTA weight multicast,
   // 7 = staggered tiles + cta_group::2 MMAs with layer-stationary weights (default for rendering, fastest)
